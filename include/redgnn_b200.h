@@ -1,0 +1,181 @@
+/*
+ * redgnn_b200.h -- C ABI of libredgnn_b200.so: the B200 (sm_100a) implementation of RED-GNN's
+ * query-conditioned relational-digraph propagation path.
+ *
+ * The reference (LARS-research/RED-GNN, Static/{transductive,inductive}) is pure Python; the
+ * "FFI" a maintainer would bind is therefore a ctypes stub.  Every entry
+ * point below names the reference code it replaces (paths relative to /root/reference/Static/).
+ *
+ * Contract:
+ *   - plain C types only: device pointers, sizes, a cudaStream_t passed as void*;
+ *   - the library allocates nothing, keeps no handles and no global state; all buffers
+ *     (graph arrays, frontier state, workspaces, outputs) are owned by the caller;
+ *   - every call is asynchronous on the given stream and never synchronises the host; the only
+ *     host read-back on the path is the caller's own copy of the 8-word `counts` block;
+ *   - return value: 0 on success, negative rg_status otherwise; nothing is thrown.
+ *
+ * Data layout in HBM
+ *   graph      : head[F], rel[F], tail[F] int32 in REFERENCE ROW ORDER (triples, then the
+ *                n_ent self-loops (e, 2*n_rel, e));  CSR-by-tail  in_ptr[n_ent+1], in_adj[F]
+ *                = (head, rel) pairs and CSR-by-head out_ptr[n_ent+1], out_adj[F] = (tail, rel)
+ *                pairs, both stable in fact order.
+ *   frontier   : the per-query node set of one layer, stored twice:
+ *                emask[n_ent][Wn] uint32, Wn = ceil(n_query/32): bit b of row e  <=> (b,e) in set
+ *                dict [n_query][We] {uint32 bits, uint32 prefix}, We = ceil(n_ent/32):
+ *                  bit (e%32) of word e/32 of row b <=> (b,e) in set;  prefix = number of set
+ *                  members that precede this word in (b, e) lexicographic order, so that
+ *                  rank(b,e) = prefix + popc(bits & ((1<<(e%32))-1)) is the row of (b,e) in the
+ *                  reference's sorted `torch.unique(dim=0)` node list.
+ */
+#ifndef REDGNN_B200_H
+#define REDGNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_ABI_VERSION 1
+
+typedef enum rg_status {
+    RG_OK = 0,
+    RG_ERR_BAD_ARG = -1,      /* null pointer, negative size, inconsistent shapes            */
+    RG_ERR_UNSUPPORTED = -2,  /* hidden_dim not in {16,32,48,64} or attn_dim > 8              */
+    RG_ERR_WORKSPACE = -3,    /* workspace smaller than rg_workspace_bytes()                  */
+    RG_ERR_TOO_LARGE = -4,    /* an index space of this call would exceed 2^31-1              */
+    RG_ERR_CUDA_BASE = -1000  /* -(1000 + cudaError_t) for a CUDA launch / API failure        */
+} rg_status;
+
+/* word indices of the int64 `counts[RG_COUNTS_WORDS]` device block written by the frontier calls */
+#define RG_COUNTS_WORDS 8
+#define RG_CNT_N_IN 0     /* unique input nodes  (rows of head_nodes)                         */
+#define RG_CNT_E 1        /* edges of this hop                                                */
+#define RG_CNT_N_OUT 2    /* rows of tail_nodes                                               */
+#define RG_CNT_ERR 3      /* bit 0: node out of range in rg_frontier_from_nodes               */
+#define RG_CNT_HEAVY 4    /* overflow flag of a heavy-segment queue (edge kernels)            */
+
+/* Static graph of one KG.  Replaces DataLoader.KG / M_sub, tKG / tM_sub (transductive/
+ * load_data.py:76-89) and tra_KG/tra_sub, ind_KG/ind_sub (inductive/load_data.py:88-98). */
+typedef struct rg_graph {
+    int32_t n_ent;
+    int32_t n_rel;           /* R; relation ids run 0..2R (2R = self-loop)                    */
+    int64_t n_fact;          /* F = rows incl. inverses and self-loops                        */
+    const int32_t *head, *rel, *tail;   /* [F] reference row order                            */
+    const int32_t *in_ptr;   /* [n_ent+1] CSR by tail                                         */
+    const int32_t *in_adj;   /* [F][2]  (head, rel), fact order inside a row                  */
+    const int32_t *out_ptr;  /* [n_ent+1] CSR by head                                         */
+    const int32_t *out_adj;  /* [F][2]  (tail, rel), fact order inside a row                  */
+} rg_graph;
+
+/* Node set of one layer (see "Data layout").  Replaces the (N,2) `nodes` LongTensor of
+ * RED_GNN_*.forward (transductive/models.py:73,78) as the carried state between hops. */
+typedef struct rg_frontier {
+    int32_t n_query;
+    int32_t n_ent;
+    uint32_t *emask;         /* [n_ent][Wn]                                                   */
+    uint32_t *dict;          /* [n_query][We][2]                                              */
+} rg_frontier;
+
+/* Segment description for the fused edge kernels.
+ * mode 0 (explicit): segment s owns adj[seg_ptr[s] .. seg_ptr[s+1]) = (peer_row, rel) pairs and
+ *                    belongs to query seg_query[s].  Used for arbitrary caller-provided edge lists
+ *                    (the public GNNLayer.forward(edges) surface, models.py:23-43).
+ * mode 1 (implicit): segment s is node (seg_query[s], seg_ent[s]); its candidate edges are the
+ *                    CSR row ent_ptr/ent_adj of that entity = (peer_entity, rel); a candidate is an
+ *                    edge iff (query, peer_entity) is in `peer_dict`, whose rank gives peer_row.
+ *                    No per-layer edge list exists in HBM on this path. */
+typedef struct rg_segments {
+    int32_t mode;
+    int32_t n_ent;                 /* implicit: dictionary row length We = ceil(n_ent/32)      */
+    int64_t n_seg;
+    const int32_t *seg_query;      /* [n_seg]                                                  */
+    const int32_t *seg_ptr;        /* explicit: [n_seg+1]                                      */
+    const int32_t *adj;            /* explicit: [E][2]; implicit: ent_adj [F][2]               */
+    const int32_t *seg_ent;        /* implicit: [n_seg]                                        */
+    const int32_t *ent_ptr;        /* implicit: [n_ent+1]                                      */
+    const uint32_t *peer_dict;     /* implicit: [n_query][We][2]                               */
+} rg_segments;
+
+/* Queue for segments longer than RG_HEAVY_CHUNK candidate slots: they are cut into chunks that
+ * other warps reduce into `partial`, then summed in chunk order (deterministic). */
+#define RG_HEAVY_CHUNK 512
+typedef struct rg_heavy {
+    int32_t max_chunks;
+    int32_t max_nodes;
+    int32_t *counters;       /* [4] zeroed by the caller: n_chunks, n_nodes, overflow, -       */
+    int32_t *chunk_seg;      /* [max_chunks]                                                   */
+    int32_t *chunk_idx;      /* [max_chunks]                                                   */
+    int32_t *node_seg;       /* [max_nodes]                                                    */
+    int32_t *node_base;      /* [max_nodes]                                                    */
+    int32_t *node_n;         /* [max_nodes]                                                    */
+    float *partial;          /* [max_chunks][row_floats]                                       */
+} rg_heavy;
+
+int rg_abi_version(void);
+const char *rg_strerror(int status);
+
+/* sizes of the caller-allocated state */
+size_t rg_frontier_emask_bytes(int32_t n_query, int32_t n_ent);
+size_t rg_frontier_dict_bytes(int32_t n_query, int32_t n_ent);
+size_t rg_workspace_bytes(int32_t n_query, int32_t n_ent, int64_t n_fact);
+
+/* ---- expansion: DataLoader.get_neighbors (transductive/load_data.py:106-131,
+ *      inductive/load_data.py:115-143) --------------------------------------------------------- */
+
+/* nodes[N][2] int64 (batch_idx, entity), any order, duplicates allowed -> frontier state.
+ * Replaces the node_1hot construction (load_data.py:115).  counts[RG_CNT_N_IN] = unique nodes. */
+int rg_frontier_from_nodes(const int64_t *nodes, int64_t n_nodes, rg_frontier *fr,
+                           int64_t *counts, void *ws, size_t ws_bytes, void *stream);
+
+/* One hop: which facts have their head in which query's frontier (M_sub.dot(node_1hot),
+ * load_data.py:116), the per-query dedup of the tails (torch.unique, :123) and the sizes
+ * counts[RG_CNT_E], counts[RG_CNT_N_OUT].  `ws` keeps the per-block edge offsets that
+ * rg_edges_emit() reads; it must be the same buffer, untouched in between. */
+int rg_frontier_step(const rg_graph *g, const rg_frontier *in, rg_frontier *out,
+                     int64_t *counts, void *ws, size_t ws_bytes, void *stream);
+
+/* Sorted unique node list of a frontier (tail_nodes, load_data.py:123): any of the three
+ * outputs may be NULL.  nodes64 is [N][2] int64, node_b / node_e are int32 [N]. */
+int rg_frontier_nodes(const rg_frontier *fr, int64_t *nodes64, int32_t *node_b, int32_t *node_e,
+                      void *stream);
+
+/* old_nodes_new_idx (load_data.py:127-129): row of every `in` node inside `out`'s node list. */
+int rg_frontier_remap(const rg_frontier *in, const rg_frontier *out, int64_t *remap64,
+                      int32_t *remap32, void *stream);
+
+/* sampled_edges[E][6] int64 = (batch, head, rel, tail, head_index, tail_index) in the
+ * reference's order (fact row ascending, batch index descending; load_data.py:117-125). */
+int rg_edges_emit(const rg_graph *g, const rg_frontier *in, const rg_frontier *out,
+                  const void *ws, size_t ws_bytes, int64_t n_edges, int64_t *edges, void *stream);
+
+/* ---- propagation: GNNLayer.forward (transductive/models.py:23-43) and its autograd ------------
+ * Attention is factorised: as8[N][8] = hidden @ Ws^T, ar8[2R+1][8] = rela @ Wr^T,
+ * aq8[n][8] = rela[q_rel] @ Wqr^T + b_qr (columns >= attn_dim are zero), w8[8] = w_alpha (zero
+ * padded).  Per edge (peer p -> segment s, relation r, query q):
+ *     alpha = sigmoid(b_alpha + sum_k w8[k] * relu(as8[p][k] + ar8[r][k] + aq8[q][k]))
+ *     agg[s] += alpha * (hidden[p] + rela[r])               (models.py:35-39)
+ * `hidden` and `as8` may both be NULL (layer 0: hidden == 0).  Segments must be grouped by the
+ * OUTPUT node; the sum runs in slot order, no atomics: bit-reproducible run to run. */
+int rg_edge_agg_fwd(const rg_segments *seg, int32_t hidden_dim, const float *hidden,
+                    const float *as8, const float *rela, const float *ar8, const float *aq8,
+                    const float *w8, const float *b_alpha, float *agg, const rg_heavy *heavy,
+                    void *stream);
+
+/* Backward of the above, segments grouped by the INPUT node p (peers are output rows):
+ *   g_hidden[p]   = sum_e alpha_e * g_agg[s_e]                      (may be NULL with hidden)
+ *   node_small[p] = { g_as8[p][0..7], sum_e g_l*relu(z)[0..7], sum_e g_l, 7 x 0 }   ([N][24])
+ *   g_rela[r]    += sum_e alpha_e * g_agg[s_e]     (fp32 atomics into a caller-zeroed buffer)
+ *   g_ar8[r]     += sum_e g_z,e                    (fp32 atomics into a caller-zeroed buffer)
+ * with g_l = <g_agg[s], hidden[p]+rela[r]> * alpha(1-alpha), g_z = g_l * w8 * [z > 0]. */
+int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hidden,
+                    const float *as8, const float *rela, const float *ar8, const float *aq8,
+                    const float *w8, const float *b_alpha, const float *g_agg, float *g_hidden,
+                    float *node_small, float *g_rela, float *g_ar8, const rg_heavy *heavy,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REDGNN_B200_H */

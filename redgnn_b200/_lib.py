@@ -1,0 +1,107 @@
+"""ctypes binding of libredgnn_b200.so (the C ABI declared in include/redgnn_b200.h).
+
+There is no fallback: if the shared library is missing the import fails loudly, and every
+compute entry point requires CUDA tensors.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libredgnn_b200.so")
+
+RG_ABI_VERSION = 1
+RG_COUNTS_WORDS = 8
+RG_CNT_N_IN, RG_CNT_E, RG_CNT_N_OUT, RG_CNT_ERR = 0, 1, 2, 3
+RG_HEAVY_CHUNK = 512
+
+
+class RgGraph(C.Structure):
+    _fields_ = [("n_ent", C.c_int32), ("n_rel", C.c_int32), ("n_fact", C.c_int64),
+                ("head", C.c_void_p), ("rel", C.c_void_p), ("tail", C.c_void_p),
+                ("in_ptr", C.c_void_p), ("in_adj", C.c_void_p),
+                ("out_ptr", C.c_void_p), ("out_adj", C.c_void_p)]
+
+
+class RgFrontier(C.Structure):
+    _fields_ = [("n_query", C.c_int32), ("n_ent", C.c_int32),
+                ("emask", C.c_void_p), ("dict", C.c_void_p)]
+
+
+class RgSegments(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("n_ent", C.c_int32), ("n_seg", C.c_int64),
+                ("seg_query", C.c_void_p), ("seg_ptr", C.c_void_p), ("adj", C.c_void_p),
+                ("seg_ent", C.c_void_p), ("ent_ptr", C.c_void_p), ("peer_dict", C.c_void_p)]
+
+
+class RgHeavy(C.Structure):
+    _fields_ = [("max_chunks", C.c_int32), ("max_nodes", C.c_int32), ("counters", C.c_void_p),
+                ("chunk_seg", C.c_void_p), ("chunk_idx", C.c_void_p), ("node_seg", C.c_void_p),
+                ("node_base", C.c_void_p), ("node_n", C.c_void_p), ("partial", C.c_void_p)]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "rg_abi_version": (C.c_int, []),
+    "rg_strerror": (C.c_char_p, [C.c_int]),
+    "rg_frontier_emask_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "rg_frontier_dict_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "rg_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "rg_frontier_from_nodes": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(RgFrontier), C.c_void_p,
+                                         C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rg_frontier_step": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier),
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "rg_frontier_nodes": (C.c_int, [C.POINTER(RgFrontier), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rg_frontier_remap": (C.c_int, [C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
+    "rg_edges_emit": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p,
+                                C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p]),
+    "rg_edge_agg_fwd": (C.c_int, [C.POINTER(RgSegments), C.c_int32] + [C.c_void_p] * 8
+                        + [C.POINTER(RgHeavy), C.c_void_p]),
+    "rg_edge_agg_bwd": (C.c_int, [C.POINTER(RgSegments), C.c_int32] + [C.c_void_p] * 12
+                        + [C.POINTER(RgHeavy), C.c_void_p]),
+}
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "redgnn_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C redgnn_b200/csrc`. There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.rg_abi_version()
+    if got != RG_ABI_VERSION:
+        raise ImportError("redgnn_b200: ABI version mismatch (library %d, binding %d)" % (got, RG_ABI_VERSION))
+    return lib
+
+
+lib = _load()
+
+
+class RgError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise RgError("libredgnn_b200: %s (status %d)" % (lib.rg_strerror(rc).decode(), rc))
+
+
+def ptr(t):
+    """Device (or host) address of a tensor, or NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RgError("redgnn_b200 kernels need CUDA tensors; got a %s tensor (no CPU fallback exists)"
+                          % t.device)

@@ -1,0 +1,561 @@
+// Fused edge kernels: the B200 replacement of GNNLayer.forward's per-edge work
+// (reference Static/transductive/models.py:23-39: gathers, attention, alpha*(hs+hr), scatter-sum)
+// and of its autograd.
+//
+// One warp owns one segment (= one output node in forward, one input node in backward).  32
+// candidate slots are probed per step (one lane each: adjacency entry + dictionary word), the
+// active ones are compacted with a ballot and then processed 8 at a time by groups of 4 lanes;
+// every lane of a group moves D/16 float4 (128-bit) pieces of the D-float rows.  The per-segment
+// sum is a fixed function of the slot order (no atomics) => bit-reproducible.
+// Segments longer than RG_HEAVY_CHUNK slots are cut into chunks via a device queue; chunk partials
+// are added back in chunk order by a fix-up kernel.
+#include "rg_common.cuh"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kBlock = kWarpsPerBlock * 32;
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+struct Slot {
+    int peer;  // row of the peer node (valid when active)
+    int rel;
+    bool active;
+};
+
+// probe candidate slot `slot` of the segment of query q
+template <bool IMPLICIT>
+__device__ __forceinline__ Slot probe_slot(const rg_segments &S, const uint2 *drow, int slot, bool valid) {
+    Slot s;
+    s.peer = 0;
+    s.rel = 0;
+    s.active = false;
+    if (valid) {
+        int2 pr = __ldg(reinterpret_cast<const int2 *>(S.adj) + slot);
+        s.rel = pr.y;
+        if (IMPLICIT) {
+            uint2 d = __ldg(drow + (pr.x >> 5));
+            uint32_t bit = 1u << (pr.x & 31);
+            s.active = (d.x & bit) != 0u;
+            s.peer = (int)(d.y + __popc(d.x & (bit - 1u)));
+        } else {
+            s.peer = pr.x;
+            s.active = true;
+        }
+    }
+    return s;
+}
+
+struct SegRange {
+    int q, lo, hi;
+};
+
+template <bool IMPLICIT>
+__device__ __forceinline__ SegRange seg_range(const rg_segments &S, int64_t seg) {
+    SegRange r;
+    r.q = __ldg(S.seg_query + seg);
+    if (IMPLICIT) {
+        int e = __ldg(S.seg_ent + seg);
+        r.lo = __ldg(S.ent_ptr + e);
+        r.hi = __ldg(S.ent_ptr + e + 1);
+    } else {
+        r.lo = __ldg(S.seg_ptr + seg);
+        r.hi = __ldg(S.seg_ptr + seg + 1);
+    }
+    return r;
+}
+
+// queue the chunks 1.. of a heavy segment (chunk 0 is done by the owner warp); warp-collective
+__device__ __forceinline__ void enqueue_heavy(const rg_heavy &H, int64_t seg, int len, int lane) {
+    const int nch = (len + RG_HEAVY_CHUNK - 1) / RG_HEAVY_CHUNK - 1;
+    int base = 0, slot = 0;
+    if (lane == 0) {
+        base = atomicAdd(&H.counters[0], nch);
+        slot = atomicAdd(&H.counters[1], 1);
+    }
+    base = __shfl_sync(RG_FULL_MASK, base, 0);
+    slot = __shfl_sync(RG_FULL_MASK, slot, 0);
+    if (base + nch > H.max_chunks || slot >= H.max_nodes) {
+        if (lane == 0) atomicExch(&H.counters[2], 1);
+        return;
+    }
+    if (lane == 0) {
+        H.node_seg[slot] = (int)seg;
+        H.node_base[slot] = base;
+        H.node_n[slot] = nch;
+    }
+    for (int c = lane; c < nch; c += 32) {
+        H.chunk_seg[base + c] = (int)seg;
+        H.chunk_idx[base + c] = c + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward: acc = sum over active slots in [lo, hi) of alpha * (hidden[peer] + rela[rel])
+// On return lanes 0..3 hold the reduced row pieces (float4 index v*4 + lane).
+// ------------------------------------------------------------------------------------------
+template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+__device__ __forceinline__ void fwd_range(const rg_segments &S, int q, int lo, int hi,
+                                          const float *__restrict__ hidden, const float *__restrict__ as8,
+                                          const float *__restrict__ rela, const float *__restrict__ ar8,
+                                          const float *__restrict__ aq8, const float *__restrict__ w8,
+                                          float b_alpha, float4 (&acc)[D / 16]) {
+    constexpr int NV = D / 16;
+    const int lane = threadIdx.x & 31, grp = lane >> 2, ql = lane & 3;
+    const float2 aq2 = __ldg(reinterpret_cast<const float2 *>(aq8 + (size_t)q * 8) + ql);
+    const float2 w2 = __ldg(reinterpret_cast<const float2 *>(w8) + ql);
+    const uint2 *drow = IMPLICIT ? reinterpret_cast<const uint2 *>(S.peer_dict) + (size_t)q * rg_words_ent(S.n_ent)
+                                 : nullptr;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (int base = lo; base < hi; base += 32) {
+        const int slot = base + lane;
+        Slot s = probe_slot<IMPLICIT>(S, drow, slot, slot < hi);
+        const unsigned m = __ballot_sync(RG_FULL_MASK, s.active);
+        const int cnt = __popc(m);
+        for (int it = 0; it < cnt; it += 8) {
+            const int k = it + grp;
+            const bool on = k < cnt;
+            const int src = on ? ((m == RG_FULL_MASK) ? k : rg_select_low(m, k)) : 0;
+            const int p = __shfl_sync(RG_FULL_MASK, s.peer, src);
+            const int r = __shfl_sync(RG_FULL_MASK, s.rel, src);
+            float4 x[NV];
+            float part = 0.f;
+            if (on) {
+                const float4 *rp = reinterpret_cast<const float4 *>(rela + (size_t)r * D);
+                float2 z = __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
+                if (HAS_HIDDEN) {
+                    const float4 *hp = reinterpret_cast<const float4 *>(hidden + (size_t)p * D);
+                    float4 h[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) h[v] = ldg4(hp + v * 4 + ql);
+                    float2 a = __ldg(reinterpret_cast<const float2 *>(as8 + (size_t)p * 8) + ql);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        float4 t = ldg4(rp + v * 4 + ql);
+                        x[v] = make_float4(h[v].x + t.x, h[v].y + t.y, h[v].z + t.z, h[v].w + t.w);
+                    }
+                    z.x += a.x;
+                    z.y += a.y;
+                } else {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) x[v] = ldg4(rp + v * 4 + ql);
+                }
+                z.x += aq2.x;
+                z.y += aq2.y;
+                part = w2.x * fmaxf(z.x, 0.f) + w2.y * fmaxf(z.y, 0.f);
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) x[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            part += __shfl_xor_sync(RG_FULL_MASK, part, 1);
+            part += __shfl_xor_sync(RG_FULL_MASK, part, 2);
+            const float alpha = on ? sigmoidf_(part + b_alpha) : 0.f;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                acc[v].x = fmaf(alpha, x[v].x, acc[v].x);
+                acc[v].y = fmaf(alpha, x[v].y, acc[v].y);
+                acc[v].z = fmaf(alpha, x[v].z, acc[v].z);
+                acc[v].w = fmaf(alpha, x[v].w, acc[v].w);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            acc[v].x += __shfl_xor_sync(RG_FULL_MASK, acc[v].x, o);
+            acc[v].y += __shfl_xor_sync(RG_FULL_MASK, acc[v].y, o);
+            acc[v].z += __shfl_xor_sync(RG_FULL_MASK, acc[v].z, o);
+            acc[v].w += __shfl_xor_sync(RG_FULL_MASK, acc[v].w, o);
+        }
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void store_row(float *dst, const float4 (&acc)[D / 16], int lane) {
+    if (lane < 4) {
+        float4 *o = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+        for (int v = 0; v < D / 16; ++v) o[v * 4 + lane] = acc[v];
+    }
+}
+
+template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+__global__ void __launch_bounds__(kBlock) k_edge_fwd(rg_segments S, const float *__restrict__ hidden,
+                                                     const float *__restrict__ as8, const float *__restrict__ rela,
+                                                     const float *__restrict__ ar8, const float *__restrict__ aq8,
+                                                     const float *__restrict__ w8, const float *__restrict__ b_alpha,
+                                                     float *__restrict__ agg, rg_heavy H, int has_heavy) {
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (seg >= S.n_seg) return;
+    SegRange r = seg_range<IMPLICIT>(S, seg);
+    int hi = r.hi;
+    if (r.hi - r.lo > RG_HEAVY_CHUNK) {
+        if (has_heavy) enqueue_heavy(H, seg, r.hi - r.lo, lane);
+        hi = r.lo + RG_HEAVY_CHUNK;
+    }
+    float4 acc[D / 16];
+    fwd_range<D, HAS_HIDDEN, IMPLICIT>(S, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), acc);
+    store_row<D>(agg + (size_t)seg * D, acc, lane);
+}
+
+template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+__global__ void __launch_bounds__(kBlock) k_edge_fwd_chunks(rg_segments S, const float *__restrict__ hidden,
+                                                            const float *__restrict__ as8,
+                                                            const float *__restrict__ rela,
+                                                            const float *__restrict__ ar8,
+                                                            const float *__restrict__ aq8,
+                                                            const float *__restrict__ w8,
+                                                            const float *__restrict__ b_alpha, rg_heavy H) {
+    const int lane = threadIdx.x & 31;
+    if (H.counters[2]) return;  // queue overflow: reported to the caller, nothing to trust
+    const int n_chunks = min(H.counters[0], H.max_chunks);
+    const int stride = gridDim.x * kWarpsPerBlock;
+    for (int c = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); c < n_chunks; c += stride) {
+        const int64_t seg = H.chunk_seg[c];
+        SegRange r = seg_range<IMPLICIT>(S, seg);
+        const int lo = r.lo + H.chunk_idx[c] * RG_HEAVY_CHUNK;
+        const int hi = min(r.hi, lo + RG_HEAVY_CHUNK);
+        float4 acc[D / 16];
+        fwd_range<D, HAS_HIDDEN, IMPLICIT>(S, r.q, lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), acc);
+        store_row<D>(H.partial + (size_t)c * D, acc, lane);
+    }
+}
+
+// rows[seg] += sum_c partial[base + c], c ascending; ROW floats per row, one warp per heavy node
+__global__ void __launch_bounds__(kBlock) k_heavy_fixup(rg_heavy H, int row_floats, float *rows_a, int a_floats,
+                                                        float *rows_b, int b_floats) {
+    const int lane = threadIdx.x & 31;
+    if (H.counters[2]) return;
+    const int n_nodes = min(H.counters[1], H.max_nodes);
+    const int stride = gridDim.x * kWarpsPerBlock;
+    for (int i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); i < n_nodes; i += stride) {
+        const size_t seg = (size_t)H.node_seg[i];
+        const int base = H.node_base[i], n = H.node_n[i];
+        for (int col = lane; col < row_floats; col += 32) {
+            float *dst = nullptr;
+            if (col < a_floats) {
+                if (rows_a) dst = rows_a + seg * a_floats + col;
+            } else if (rows_b) {
+                dst = rows_b + seg * b_floats + (col - a_floats);
+            }
+            if (!dst) continue;
+            float v = *dst;
+            for (int c = 0; c < n; ++c) v += H.partial[(size_t)(base + c) * row_floats + col];
+            *dst = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, grouped by the input node.  Per-segment results (after the group reduction, valid in
+// lanes 0..3): G = sum alpha*g_agg[peer]; small = {Z2 (g_as8 pair), WZ2, GL}.
+// ------------------------------------------------------------------------------------------
+struct BwdSmall {
+    float2 z, wz;
+    float gl;
+};
+
+template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+__device__ __forceinline__ void bwd_range(const rg_segments &S, int64_t seg, int q, int lo, int hi,
+                                          const float *__restrict__ hidden, const float *__restrict__ as8,
+                                          const float *__restrict__ rela, const float *__restrict__ ar8,
+                                          const float *__restrict__ aq8, const float *__restrict__ w8,
+                                          float b_alpha, const float *__restrict__ g_agg, float *g_rela,
+                                          float *g_ar8, float4 (&G)[D / 16], BwdSmall &sm) {
+    constexpr int NV = D / 16;
+    const int lane = threadIdx.x & 31, grp = lane >> 2, ql = lane & 3;
+    const float2 w2 = __ldg(reinterpret_cast<const float2 *>(w8) + ql);
+    float2 zbase = __ldg(reinterpret_cast<const float2 *>(aq8 + (size_t)q * 8) + ql);
+    float4 hs[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) hs[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HAS_HIDDEN) {
+        const float4 *hp = reinterpret_cast<const float4 *>(hidden + (size_t)seg * D);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) hs[v] = ldg4(hp + v * 4 + ql);
+        float2 a = __ldg(reinterpret_cast<const float2 *>(as8 + (size_t)seg * 8) + ql);
+        zbase.x += a.x;
+        zbase.y += a.y;
+    }
+    const uint2 *drow = IMPLICIT ? reinterpret_cast<const uint2 *>(S.peer_dict) + (size_t)q * rg_words_ent(S.n_ent)
+                                 : nullptr;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) G[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.z = make_float2(0.f, 0.f);
+    sm.wz = make_float2(0.f, 0.f);
+    sm.gl = 0.f;
+
+    for (int base = lo; base < hi; base += 32) {
+        const int slot = base + lane;
+        Slot s = probe_slot<IMPLICIT>(S, drow, slot, slot < hi);
+        const unsigned m = __ballot_sync(RG_FULL_MASK, s.active);
+        const int cnt = __popc(m);
+        for (int it = 0; it < cnt; it += 8) {
+            const int k = it + grp;
+            const bool on = k < cnt;
+            const int src = on ? ((m == RG_FULL_MASK) ? k : rg_select_low(m, k)) : 0;
+            const int p = __shfl_sync(RG_FULL_MASK, s.peer, src);
+            const int r = __shfl_sync(RG_FULL_MASK, s.rel, src);
+            float4 g[NV];
+            float2 z = zbase;
+            float dot = 0.f, part = 0.f;
+            if (on) {
+                const float4 *gp = reinterpret_cast<const float4 *>(g_agg + (size_t)p * D);
+                const float4 *rp = reinterpret_cast<const float4 *>(rela + (size_t)r * D);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) g[v] = ldg4(gp + v * 4 + ql);
+                float2 a = __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    float4 t = ldg4(rp + v * 4 + ql);
+                    dot = fmaf(g[v].x, hs[v].x + t.x, dot);
+                    dot = fmaf(g[v].y, hs[v].y + t.y, dot);
+                    dot = fmaf(g[v].z, hs[v].z + t.z, dot);
+                    dot = fmaf(g[v].w, hs[v].w + t.w, dot);
+                }
+                z.x += a.x;
+                z.y += a.y;
+                part = w2.x * fmaxf(z.x, 0.f) + w2.y * fmaxf(z.y, 0.f);
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            part += __shfl_xor_sync(RG_FULL_MASK, part, 1);
+            part += __shfl_xor_sync(RG_FULL_MASK, part, 2);
+            dot += __shfl_xor_sync(RG_FULL_MASK, dot, 1);
+            dot += __shfl_xor_sync(RG_FULL_MASK, dot, 2);
+            if (on) {
+                const float alpha = sigmoidf_(part + b_alpha);
+                const float gl = dot * alpha * (1.f - alpha);
+                float2 gz = make_float2(z.x > 0.f ? gl * w2.x : 0.f, z.y > 0.f ? gl * w2.y : 0.f);
+                sm.z.x += gz.x;
+                sm.z.y += gz.y;
+                sm.wz.x = fmaf(gl, fmaxf(z.x, 0.f), sm.wz.x);
+                sm.wz.y = fmaf(gl, fmaxf(z.y, 0.f), sm.wz.y);
+                sm.gl += gl;
+                float4 *gr = reinterpret_cast<float4 *>(g_rela + (size_t)r * D);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    float4 ag = make_float4(alpha * g[v].x, alpha * g[v].y, alpha * g[v].z, alpha * g[v].w);
+                    G[v].x += ag.x;
+                    G[v].y += ag.y;
+                    G[v].z += ag.z;
+                    G[v].w += ag.w;
+                    atomicAdd(gr + v * 4 + ql, ag);
+                }
+                atomicAdd(reinterpret_cast<float2 *>(g_ar8 + (size_t)r * 8) + ql, gz);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            G[v].x += __shfl_xor_sync(RG_FULL_MASK, G[v].x, o);
+            G[v].y += __shfl_xor_sync(RG_FULL_MASK, G[v].y, o);
+            G[v].z += __shfl_xor_sync(RG_FULL_MASK, G[v].z, o);
+            G[v].w += __shfl_xor_sync(RG_FULL_MASK, G[v].w, o);
+        }
+        sm.z.x += __shfl_xor_sync(RG_FULL_MASK, sm.z.x, o);
+        sm.z.y += __shfl_xor_sync(RG_FULL_MASK, sm.z.y, o);
+        sm.wz.x += __shfl_xor_sync(RG_FULL_MASK, sm.wz.x, o);
+        sm.wz.y += __shfl_xor_sync(RG_FULL_MASK, sm.wz.y, o);
+        sm.gl += __shfl_xor_sync(RG_FULL_MASK, sm.gl, o);
+    }
+}
+
+// node_small row layout: [0..7] g_as8, [8..15] sum g_l*relu(z), [16] sum g_l, [17..23] zero
+__device__ __forceinline__ void store_small(float *dst, const BwdSmall &sm, int lane) {
+    if (lane < 4) {
+        float2 *o = reinterpret_cast<float2 *>(dst);
+        o[lane] = sm.z;
+        o[4 + lane] = sm.wz;
+        o[8 + lane] = make_float2(lane == 0 ? sm.gl : 0.f, 0.f);
+    }
+}
+
+template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+__global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float *__restrict__ hidden,
+                                                     const float *__restrict__ as8, const float *__restrict__ rela,
+                                                     const float *__restrict__ ar8, const float *__restrict__ aq8,
+                                                     const float *__restrict__ w8, const float *__restrict__ b_alpha,
+                                                     const float *__restrict__ g_agg, float *g_hidden,
+                                                     float *node_small, float *g_rela, float *g_ar8, rg_heavy H,
+                                                     int has_heavy) {
+    const int lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (seg >= S.n_seg) return;
+    SegRange r = seg_range<IMPLICIT>(S, seg);
+    int hi = r.hi;
+    if (r.hi - r.lo > RG_HEAVY_CHUNK) {
+        if (has_heavy) enqueue_heavy(H, seg, r.hi - r.lo, lane);
+        hi = r.lo + RG_HEAVY_CHUNK;
+    }
+    float4 G[D / 16];
+    BwdSmall sm;
+    bwd_range<D, HAS_HIDDEN, IMPLICIT>(S, seg, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), g_agg,
+                                       g_rela, g_ar8, G, sm);
+    if (g_hidden) store_row<D>(g_hidden + (size_t)seg * D, G, lane);
+    store_small(node_small + (size_t)seg * 24, sm, lane);
+}
+
+template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+__global__ void __launch_bounds__(kBlock) k_edge_bwd_chunks(rg_segments S, const float *__restrict__ hidden,
+                                                            const float *__restrict__ as8,
+                                                            const float *__restrict__ rela,
+                                                            const float *__restrict__ ar8,
+                                                            const float *__restrict__ aq8,
+                                                            const float *__restrict__ w8,
+                                                            const float *__restrict__ b_alpha,
+                                                            const float *__restrict__ g_agg, float *g_rela,
+                                                            float *g_ar8, rg_heavy H) {
+    const int lane = threadIdx.x & 31;
+    if (H.counters[2]) return;
+    const int n_chunks = min(H.counters[0], H.max_chunks);
+    const int stride = gridDim.x * kWarpsPerBlock;
+    for (int c = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); c < n_chunks; c += stride) {
+        const int64_t seg = H.chunk_seg[c];
+        SegRange r = seg_range<IMPLICIT>(S, seg);
+        const int lo = r.lo + H.chunk_idx[c] * RG_HEAVY_CHUNK;
+        const int hi = min(r.hi, lo + RG_HEAVY_CHUNK);
+        float4 G[D / 16];
+        BwdSmall sm;
+        bwd_range<D, HAS_HIDDEN, IMPLICIT>(S, seg, r.q, lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), g_agg,
+                                           g_rela, g_ar8, G, sm);
+        float *row = H.partial + (size_t)c * (D + 24);
+        store_row<D>(row, G, lane);
+        store_small(row + D, sm, lane);
+    }
+}
+
+int check_segments(const rg_segments *s) {
+    if (!s || s->n_seg < 0 || !s->seg_query || !s->adj) return RG_ERR_BAD_ARG;
+    if (s->mode == 0) {
+        if (!s->seg_ptr) return RG_ERR_BAD_ARG;
+    } else if (s->mode == 1) {
+        if (!s->seg_ent || !s->ent_ptr || !s->peer_dict || s->n_ent <= 0) return RG_ERR_BAD_ARG;
+    } else {
+        return RG_ERR_BAD_ARG;
+    }
+    if (rg_cdiv(s->n_seg, kWarpsPerBlock) >= (int64_t)INT32_MAX) return RG_ERR_TOO_LARGE;
+    return RG_OK;
+}
+
+int check_heavy(const rg_heavy *h) {
+    if (!h) return RG_OK;
+    if (h->max_chunks < 0 || h->max_nodes < 0 || !h->counters) return RG_ERR_BAD_ARG;
+    if (h->max_chunks > 0 && (!h->chunk_seg || !h->chunk_idx || !h->partial)) return RG_ERR_BAD_ARG;
+    if (h->max_nodes > 0 && (!h->node_seg || !h->node_base || !h->node_n)) return RG_ERR_BAD_ARG;
+    return RG_OK;
+}
+
+constexpr int kHeavyGrid = 148 * 4;
+
+template <int D, bool HH, bool IM>
+int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, const float *rela, const float *ar8,
+               const float *aq8, const float *w8, const float *b_alpha, float *agg, const rg_heavy *heavy,
+               cudaStream_t st) {
+    rg_heavy H = {};
+    const int has_heavy = heavy && heavy->max_chunks > 0 && heavy->max_nodes > 0;
+    if (has_heavy) H = *heavy;
+    if (seg->n_seg == 0) return RG_OK;
+    const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
+    k_edge_fwd<D, HH, IM><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, agg, H, has_heavy);
+    RG_LAUNCH_CHECK();
+    if (has_heavy) {
+        k_edge_fwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, H);
+        RG_LAUNCH_CHECK();
+        k_heavy_fixup<<<kHeavyGrid, kBlock, 0, st>>>(H, D, agg, D, nullptr, 0);
+        RG_LAUNCH_CHECK();
+    }
+    return RG_OK;
+}
+
+template <int D, bool HH, bool IM>
+int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, const float *rela, const float *ar8,
+               const float *aq8, const float *w8, const float *b_alpha, const float *g_agg, float *g_hidden,
+               float *node_small, float *g_rela, float *g_ar8, const rg_heavy *heavy, cudaStream_t st) {
+    rg_heavy H = {};
+    const int has_heavy = heavy && heavy->max_chunks > 0 && heavy->max_nodes > 0;
+    if (has_heavy) H = *heavy;
+    if (seg->n_seg == 0) return RG_OK;
+    const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
+    k_edge_bwd<D, HH, IM><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, g_hidden,
+                                                   node_small, g_rela, g_ar8, H, has_heavy);
+    RG_LAUNCH_CHECK();
+    if (has_heavy) {
+        k_edge_bwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha,
+                                                                    g_agg, g_rela, g_ar8, H);
+        RG_LAUNCH_CHECK();
+        k_heavy_fixup<<<kHeavyGrid, kBlock, 0, st>>>(H, D + 24, g_hidden, D, node_small, 24);
+        RG_LAUNCH_CHECK();
+    }
+    return RG_OK;
+}
+
+#define RG_DISPATCH_D(D_, CALL)              \
+    switch (D_) {                            \
+        case 16: { constexpr int DD = 16; CALL; } break; \
+        case 32: { constexpr int DD = 32; CALL; } break; \
+        case 48: { constexpr int DD = 48; CALL; } break; \
+        case 64: { constexpr int DD = 64; CALL; } break; \
+        default: return RG_ERR_UNSUPPORTED;  \
+    }
+
+}  // namespace
+
+extern "C" {
+
+int rg_edge_agg_fwd(const rg_segments *seg, int32_t hidden_dim, const float *hidden, const float *as8,
+                    const float *rela, const float *ar8, const float *aq8, const float *w8, const float *b_alpha,
+                    float *agg, const rg_heavy *heavy, void *stream) {
+    int rc = check_segments(seg);
+    if (rc) return rc;
+    rc = check_heavy(heavy);
+    if (rc) return rc;
+    if (!rela || !ar8 || !aq8 || !w8 || !b_alpha || !agg) return RG_ERR_BAD_ARG;
+    if ((hidden == nullptr) != (as8 == nullptr)) return RG_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool hh = hidden != nullptr, im = seg->mode == 1;
+#define RG_FWD(HH, IM) \
+    RG_DISPATCH_D(hidden_dim, rc = (launch_fwd<DD, HH, IM>(seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, agg, heavy, st)))
+    if (hh && im) { RG_FWD(true, true); }
+    else if (hh && !im) { RG_FWD(true, false); }
+    else if (!hh && im) { RG_FWD(false, true); }
+    else { RG_FWD(false, false); }
+#undef RG_FWD
+    return rc;
+}
+
+int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hidden, const float *as8,
+                    const float *rela, const float *ar8, const float *aq8, const float *w8, const float *b_alpha,
+                    const float *g_agg, float *g_hidden, float *node_small, float *g_rela, float *g_ar8,
+                    const rg_heavy *heavy, void *stream) {
+    int rc = check_segments(seg);
+    if (rc) return rc;
+    rc = check_heavy(heavy);
+    if (rc) return rc;
+    if (!rela || !ar8 || !aq8 || !w8 || !b_alpha || !g_agg || !node_small || !g_rela || !g_ar8)
+        return RG_ERR_BAD_ARG;
+    if ((hidden == nullptr) != (as8 == nullptr)) return RG_ERR_BAD_ARG;
+    if (!hidden && g_hidden) return RG_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool hh = hidden != nullptr, im = seg->mode == 1;
+#define RG_BWD(HH, IM)                                                                                             \
+    RG_DISPATCH_D(hidden_dim, rc = (launch_bwd<DD, HH, IM>(seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,   \
+                                                           g_hidden, node_small, g_rela, g_ar8, heavy, st)))
+    if (hh && im) { RG_BWD(true, true); }
+    else if (hh && !im) { RG_BWD(true, false); }
+    else if (!hh && im) { RG_BWD(false, true); }
+    else { RG_BWD(false, false); }
+#undef RG_BWD
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,290 @@
+"""Drop-in DataLoaders: same files, attributes and methods as the reference's
+Static/transductive/load_data.py and Static/inductive/load_data.py `DataLoader`, with the graph
+held on the GPU (`DeviceGraph`) and `get_neighbors` served by the CUDA expansion kernels.
+
+Only the graph store and `get_neighbors` are on the accelerated path; the text parsing, query
+grouping, filters and batching below are host-side harness kept behaviour-compatible so that the
+reference's base_model.py / train.py run unchanged.
+"""
+from collections import defaultdict
+import os
+
+import numpy as np
+import torch
+
+from .graph import DeviceGraph
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        return None
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def _read_id_table(path, with_id):
+    table = {}
+    with open(path) as f:
+        for k, line in enumerate(f):
+            if with_id:
+                name, idx = line.strip().split()
+                table[name] = int(idx)
+            else:
+                table[line.strip()] = k
+    return table
+
+
+def _read_raw_triples(path, ent, rel):
+    out = []
+    with open(path) as f:
+        for line in f:
+            h, r, t = line.strip().split()
+            out.append([ent[h], rel[r], ent[t]])
+    return out
+
+
+def _group_queries(triples):
+    """load_query (transductive/load_data.py:91-104): queries keyed by (h, r) in sorted order."""
+    triples.sort(key=lambda x: (x[0], x[1]))
+    table = defaultdict(list)
+    for h, r, t in triples:
+        table[(h, r)].append(t)
+    return list(table.keys()), [np.array(v) for v in table.values()]
+
+
+def _ragged(lst):
+    arr = np.empty(len(lst), dtype=object)
+    for i, a in enumerate(lst):
+        arr[i] = a
+    return arr
+
+
+def _multi_hot(answers, batch_idx, n_ent):
+    objs = np.zeros((len(batch_idx), n_ent))
+    for i, k in enumerate(batch_idx):
+        objs[i][answers[k]] = 1
+    return objs
+
+
+class _GraphSlot(object):
+    """Host triples of one KG + its lazily built device copy."""
+
+    def __init__(self, triples, n_ent, n_rel):
+        self.triples = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+        self.n_ent, self.n_rel = n_ent, n_rel
+        self.n_fact = len(self.triples) + n_ent
+        self._dev = {}
+
+    def on(self, device):
+        key = str(device)
+        g = self._dev.get(key)
+        if g is None:
+            g = DeviceGraph(self.triples, self.n_ent, self.n_rel, device)
+            self._dev = {key: g}
+        return g
+
+    def kg(self):
+        """The reference's KG array ([triples ; self-loops]) as int64."""
+        ids = np.arange(self.n_ent, dtype=np.int64)
+        loops = np.stack([ids, np.full_like(ids, 2 * self.n_rel), ids], axis=1)
+        return np.concatenate([self.triples, loops], axis=0)
+
+
+class TransductiveLoader(object):
+    """Static/transductive/load_data.py:8-164."""
+
+    def __init__(self, task_dir, device=None):
+        self.task_dir = task_dir
+        self.device = device if device is not None else _default_device()
+        self.entity2id = _read_id_table(os.path.join(task_dir, 'entities.txt'), False)
+        self.relation2id = _read_id_table(os.path.join(task_dir, 'relations.txt'), False)
+        self.n_ent = len(self.entity2id)
+        self.n_rel = len(self.relation2id)
+
+        self.filters = defaultdict(lambda: set())
+        self.fact_triple = self.read_triples('facts.txt')
+        self.train_triple = self.read_triples('train.txt')
+        self.valid_triple = self.read_triples('valid.txt')
+        self.test_triple = self.read_triples('test.txt')
+
+        self.fact_data = self.double_triple(self.fact_triple)
+        self.train_data = np.array(self.double_triple(self.train_triple))
+        self.valid_data = self.double_triple(self.valid_triple)
+        self.test_data = self.double_triple(self.test_triple)
+
+        self.load_graph(self.fact_data)
+        self.load_test_graph(self.double_triple(self.fact_triple) + self.double_triple(self.train_triple))
+
+        self.valid_q, self.valid_a = _group_queries(self.valid_data)
+        self.test_q, self.test_a = _group_queries(self.test_data)
+        self.valid_a, self.test_a = _ragged(self.valid_a), _ragged(self.test_a)
+
+        self.n_train = len(self.train_data)
+        self.n_valid = len(self.valid_q)
+        self.n_test = len(self.test_q)
+
+        for filt in self.filters:
+            self.filters[filt] = list(self.filters[filt])
+
+        print('n_train:', self.n_train, 'n_valid:', self.n_valid, 'n_test:', self.n_test)
+
+    def read_triples(self, filename):
+        triples = _read_raw_triples(os.path.join(self.task_dir, filename), self.entity2id, self.relation2id)
+        for h, r, t in triples:
+            self.filters[(h, r)].add(t)
+            self.filters[(t, r + self.n_rel)].add(h)
+        return triples
+
+    def double_triple(self, triples):
+        """Inverse triples appended as one block after the originals (load_data.py:69-74)."""
+        return list(triples) + [[t, r + self.n_rel, h] for h, r, t in triples]
+
+    def load_graph(self, triples):
+        self._train_graph = _GraphSlot(triples, self.n_ent, self.n_rel)
+        self.n_fact = self._train_graph.n_fact
+
+    def load_test_graph(self, triples):
+        self._test_graph = _GraphSlot(triples, self.n_ent, self.n_rel)
+        self.tn_fact = self._test_graph.n_fact
+
+    @property
+    def KG(self):
+        return self._train_graph.kg()
+
+    @property
+    def tKG(self):
+        return self._test_graph.kg()
+
+    def graph_for(self, mode, device=None):
+        slot = self._train_graph if mode == 'train' else self._test_graph     # load_data.py:107-112
+        return slot.on(device if device is not None else self.device)
+
+    def n_ent_for(self, mode):
+        return self.n_ent
+
+    def get_neighbors(self, nodes, mode='train'):
+        return self.graph_for(mode).get_neighbors(nodes)
+
+    def get_batch(self, batch_idx, steps=2, data='train'):
+        if data == 'train':
+            return np.array(self.train_data)[batch_idx]
+        if data == 'valid':
+            query, answer = np.array(self.valid_q), self.valid_a
+        if data == 'test':
+            query, answer = np.array(self.test_q), self.test_a
+        subs = query[batch_idx, 0]
+        rels = query[batch_idx, 1]
+        return subs, rels, _multi_hot(answer, batch_idx, self.n_ent)
+
+    def shuffle_train(self):
+        """load_data.py:152-164: re-split facts+train 3:1 with np.random and rebuild the graph."""
+        all_triple = np.concatenate([np.array(self.fact_triple), np.array(self.train_triple)], axis=0)
+        n_all = len(all_triple)
+        all_triple = all_triple[np.random.permutation(n_all)]
+        self.fact_data = self.double_triple(all_triple[:n_all * 3 // 4].tolist())
+        self.train_data = np.array(self.double_triple(all_triple[n_all * 3 // 4:].tolist()))
+        self.n_train = len(self.train_data)
+        self.load_graph(self.fact_data)
+
+
+class InductiveLoader(object):
+    """Static/inductive/load_data.py:8-197."""
+
+    def __init__(self, task_dir, device=None):
+        self.trans_dir = task_dir
+        self.ind_dir = task_dir + '_ind'
+        self.device = device if device is not None else _default_device()
+        self.entity2id = _read_id_table(os.path.join(task_dir, 'entities.txt'), True)
+        self.relation2id = _read_id_table(os.path.join(task_dir, 'relations.txt'), True)
+        self.entity2id_ind = _read_id_table(os.path.join(self.ind_dir, 'entities.txt'), True)
+        id2relation = list(self.relation2id.keys())
+        self.id2relation = id2relation + [r + '_inv' for r in id2relation] + ['idd']
+
+        self.n_ent = len(self.entity2id)
+        self.n_rel = len(self.relation2id)
+        self.n_ent_ind = len(self.entity2id_ind)
+
+        self.tra_train = self.read_triples(self.trans_dir, 'train.txt')
+        self.tra_valid = self.read_triples(self.trans_dir, 'valid.txt')
+        self.tra_test = self.read_triples(self.trans_dir, 'test.txt')
+        self.ind_train = self.read_triples(self.ind_dir, 'train.txt', 'inductive')
+        self.ind_valid = self.read_triples(self.ind_dir, 'valid.txt', 'inductive')
+        self.ind_test = self.read_triples(self.ind_dir, 'test.txt', 'inductive')
+
+        self.val_filters = self.get_filter('valid')
+        self.tst_filters = self.get_filter('test')
+        for filt in self.val_filters:
+            self.val_filters[filt] = list(self.val_filters[filt])
+        for filt in self.tst_filters:
+            self.tst_filters[filt] = list(self.tst_filters[filt])
+
+        self._tra_graph = self.load_graph(self.tra_train)
+        self._ind_graph = self.load_graph(self.ind_train, 'inductive')
+
+        self.tra_train = np.array(self.tra_valid)
+        self.tra_val_qry, self.tra_val_ans = _group_queries(self.tra_test)
+        self.ind_val_qry, self.ind_val_ans = _group_queries(self.ind_valid)
+        self.ind_tst_qry, self.ind_tst_ans = _group_queries(self.ind_test)
+        self.valid_q, self.valid_a = self.tra_val_qry, _ragged(self.tra_val_ans)
+        self.test_q = self.ind_val_qry + self.ind_tst_qry
+        self.test_a = _ragged(self.ind_val_ans + self.ind_tst_ans)
+
+        self.n_train = len(self.tra_train)
+        self.n_valid = len(self.valid_q)
+        self.n_test = len(self.test_q)
+
+        print('n_train:', self.n_train, 'n_valid:', self.n_valid, 'n_test:', self.n_test)
+
+    def read_triples(self, directory, filename, mode='transductive'):
+        """(h,r,t) and its inverse interleaved per line (inductive/load_data.py:76-86)."""
+        ent = self.entity2id if mode == 'transductive' else self.entity2id_ind
+        out = []
+        for h, r, t in _read_raw_triples(os.path.join(directory, filename), ent, self.relation2id):
+            out.append([h, r, t])
+            out.append([t, r + self.n_rel, h])
+        return out
+
+    def load_graph(self, triples, mode='transductive'):
+        n_ent = self.n_ent if mode == 'transductive' else self.n_ent_ind
+        return _GraphSlot(triples, n_ent, self.n_rel)
+
+    @property
+    def tra_KG(self):
+        return self._tra_graph.kg()
+
+    @property
+    def ind_KG(self):
+        return self._ind_graph.kg()
+
+    def graph_for(self, mode, device=None):
+        slot = self._tra_graph if mode == 'transductive' else self._ind_graph    # :118-125
+        return slot.on(device if device is not None else self.device)
+
+    def n_ent_for(self, mode):
+        return self.n_ent if mode == 'transductive' else self.n_ent_ind
+
+    def get_neighbors(self, nodes, mode='transductive'):
+        return self.graph_for(mode).get_neighbors(nodes)
+
+    def get_batch(self, batch_idx, steps=2, data='train'):
+        if data == 'train':
+            return self.tra_train[batch_idx]
+        if data == 'valid':
+            query, answer, n_ent = np.array(self.valid_q), self.valid_a, self.n_ent
+        if data == 'test':
+            query, answer, n_ent = np.array(self.test_q), self.test_a, self.n_ent_ind
+        subs = query[batch_idx, 0]
+        rels = query[batch_idx, 1]
+        return subs, rels, _multi_hot(answer, batch_idx, n_ent)
+
+    def shuffle_train(self):
+        rand_idx = np.random.permutation(self.n_train)
+        self.tra_train = self.tra_train[rand_idx]
+
+    def get_filter(self, data='valid'):
+        filters = defaultdict(lambda: set())
+        groups = (self.tra_train, self.tra_valid, self.tra_test) if data == 'valid' \
+            else (self.ind_train, self.ind_valid, self.ind_test)
+        for triples in groups:
+            for h, r, t in triples:
+                filters[(h, r)].add(t)
+        return filters

@@ -1,0 +1,141 @@
+"""Host-side mirror of the reference's model surface for the propagation path.
+
+`GNNLayer` and `RedGNN` (base of RED_GNN_trans / RED_GNN_induc) keep the reference's constructor
+and forward signatures and parameter names (reference Static/transductive/models.py:5-89,
+Static/inductive/models.py:5-89), so a reference `state_dict` loads unchanged and
+Static/*/base_model.py / train.py run unmodified on top of them.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .ops import Segments, edge_aggregate
+
+SUPPORTED_DIMS = (16, 32, 48, 64)
+
+
+def _pad8(x):
+    """Pad the last (attention) dimension to the kernels' fixed width of 8 with zeros."""
+    a = x.shape[-1]
+    return x if a == 8 else F.pad(x, (0, 8 - a))
+
+
+class GNNLayer(torch.nn.Module):
+    """models.py:5-43.  Same parameters; the per-edge work runs in the fused CUDA kernels."""
+
+    def __init__(self, in_dim, out_dim, attn_dim, n_rel, act=lambda x: x):
+        super(GNNLayer, self).__init__()
+        if in_dim not in SUPPORTED_DIMS:
+            raise ValueError("redgnn_b200: hidden_dim must be one of %s, got %d" % (SUPPORTED_DIMS, in_dim))
+        if not 1 <= attn_dim <= 8:
+            raise ValueError("redgnn_b200: attn_dim must be in 1..8, got %d" % attn_dim)
+        self.n_rel = n_rel
+        self.in_dim = in_dim
+        self.out_dim = out_dim
+        self.attn_dim = attn_dim
+        self.act = act
+
+        self.rela_embed = nn.Embedding(2 * n_rel + 1, in_dim)
+        self.Ws_attn = nn.Linear(in_dim, attn_dim, bias=False)
+        self.Wr_attn = nn.Linear(in_dim, attn_dim, bias=False)
+        self.Wqr_attn = nn.Linear(in_dim, attn_dim)
+        self.w_alpha = nn.Linear(attn_dim, 1)
+        self.W_h = nn.Linear(in_dim, out_dim, bias=False)
+
+    def propagate(self, q_rel, hidden, fwd_seg, bwd_seg):
+        """Shared core.  hidden may be None (== all zeros, layer 0).  The attention projections are
+        per node / per relation / per query (tiny dense maps, left to torch + autograd); everything
+        per edge is one fused kernel forward and one backward."""
+        rela = self.rela_embed.weight
+        as8 = _pad8(self.Ws_attn(hidden)) if hidden is not None else None
+        ar8 = _pad8(self.Wr_attn(rela))
+        aq8 = _pad8(self.Wqr_attn(rela[q_rel]))
+        w8 = _pad8(self.w_alpha.weight).reshape(8)
+        agg = edge_aggregate(hidden, as8, rela, ar8, aq8, w8, self.w_alpha.bias, fwd_seg, bwd_seg)
+        return self.act(self.W_h(agg))
+
+    def forward(self, q_sub, q_rel, hidden, edges, n_node, old_nodes_new_idx):
+        """models.py:23-43 for a caller-provided edge list
+        edges[E,6] = (batch_idx, head, rela, tail, old_idx, new_idx)."""
+        _lib.require_cuda(hidden, edges)
+        sub, rel, obj, r_idx = edges[:, 4], edges[:, 2], edges[:, 5], edges[:, 0]
+        fwd_seg = Segments.explicit(obj, sub, rel, r_idx, int(n_node))
+        bwd_seg = Segments.explicit(sub, obj, rel, r_idx, int(hidden.shape[0])) if torch.is_grad_enabled() else None
+        return self.propagate(q_rel, hidden, fwd_seg, bwd_seg)
+
+
+class RedGNN(torch.nn.Module):
+    """Common body of RED_GNN_trans / RED_GNN_induc (models.py:45-89)."""
+
+    def __init__(self, params, loader):
+        super(RedGNN, self).__init__()
+        self.n_layer = params.n_layer
+        self.hidden_dim = params.hidden_dim
+        self.attn_dim = params.attn_dim
+        self.n_rel = params.n_rel
+        self.loader = loader
+        acts = {'relu': nn.ReLU(), 'tanh': torch.tanh, 'idd': lambda x: x}
+        act = acts[params.act]
+
+        self.gnn_layers = nn.ModuleList([GNNLayer(self.hidden_dim, self.hidden_dim, self.attn_dim, self.n_rel, act=act)
+                                         for _ in range(self.n_layer)])
+        self.dropout = nn.Dropout(params.dropout)
+        self.W_final = nn.Linear(self.hidden_dim, 1, bias=False)
+        self.gate = nn.GRU(self.hidden_dim, self.hidden_dim)
+        self.last_stats = None
+
+    # single-step GRU cell with the nn.GRU parameters, in exact fp32 (cuDNN's RNN path may pick
+    # TF32 tensor-core math, which breaks the 1e-4 parity bound)
+    def _gate(self, x, h):
+        g = self.gate
+        gi = F.linear(x, g.weight_ih_l0, g.bias_ih_l0)
+        gh = F.linear(h, g.weight_hh_l0, g.bias_hh_l0)
+        i_r, i_z, i_n = gi.chunk(3, dim=1)
+        h_r, h_z, h_n = gh.chunk(3, dim=1)
+        r = torch.sigmoid(i_r + h_r)
+        z = torch.sigmoid(i_z + h_z)
+        n = torch.tanh(i_n + r * h_n)
+        return (1.0 - z) * n + z * h
+
+    def _run(self, subs, rels, graph, n_ent_out):
+        dev = self.W_final.weight.device
+        if dev.type != 'cuda':
+            raise _lib.RgError("redgnn_b200: the model must live on a CUDA device (call .cuda()); no CPU path exists")
+        n = len(subs)
+        d = self.hidden_dim
+        q_sub = torch.as_tensor(np.asarray(subs), dtype=torch.int64).to(dev, non_blocking=True)
+        q_rel = torch.as_tensor(np.asarray(rels), dtype=torch.int64).to(dev, non_blocking=True)
+        need_grad = torch.is_grad_enabled()
+
+        batch = torch.arange(n, device=dev)
+        fr = graph.frontier_from_nodes(torch.stack([batch, q_sub], dim=1), n)
+        node_b, node_e = batch.to(torch.int32), q_sub.to(torch.int32)
+        n_nodes = n
+        h0 = torch.zeros((n, d), device=dev)
+        hidden = None
+        edges_per_layer = []
+        for i in range(self.n_layer):
+            fr_next = graph.step(fr)
+            _, n_edges, n_next, err = fr_next.read_counts(also=fr if i == 0 else None)
+            if err:
+                raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % graph.n_ent)
+            nb, ne = fr_next.nodes32(n_next)
+            remap = fr.remap_to(fr_next, n_nodes)
+            fwd_seg = Segments.implicit(nb, ne, graph.in_ptr, graph.in_adj, fr, graph.heavy_in)
+            bwd_seg = Segments.implicit(node_b, node_e, graph.out_ptr, graph.out_adj, fr_next, graph.heavy_out) \
+                if need_grad else None
+            hidden = self.gnn_layers[i].propagate(q_rel, hidden, fwd_seg, bwd_seg)
+            h0 = torch.zeros((n_next, d), device=dev).index_copy_(0, remap, h0)
+            hidden = self.dropout(hidden)
+            hidden = self._gate(hidden, h0)
+            h0 = hidden
+            fr, node_b, node_e, n_nodes = fr_next, nb, ne, n_next
+            edges_per_layer.append(n_edges)
+
+        scores = self.W_final(hidden).squeeze(-1)
+        scores_all = torch.zeros((n, n_ent_out), device=dev)
+        scores_all[node_b.long(), node_e.long()] = scores
+        self.last_stats = {"edges": edges_per_layer, "nodes": n_nodes}
+        return scores_all

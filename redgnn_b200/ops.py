@@ -1,0 +1,145 @@
+"""autograd wrapper of the fused edge kernels (rg_edge_agg_fwd / rg_edge_agg_bwd).
+
+Replaces the per-edge part of GNNLayer.forward (reference Static/transductive/models.py:29-39:
+hidden[sub], rela_embed(rel), rela_embed(q_rel)[r_idx], attention, alpha*(hs+hr), scatter-sum)
+and what autograd would do for it (index_select / embedding backward / scatter backward).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+
+class Segments(object):
+    """Python owner of an rg_segments description (see include/redgnn_b200.h)."""
+
+    def __init__(self, mode, n_seg, seg_query, adj, n_ent=0, seg_ptr=None, seg_ent=None, ent_ptr=None,
+                 peer_dict=None, heavy_bound=(0, 0)):
+        self.mode, self.n_seg, self.n_ent = int(mode), int(n_seg), int(n_ent)
+        self.seg_query, self.adj = seg_query, adj
+        self.seg_ptr, self.seg_ent, self.ent_ptr, self.peer_dict = seg_ptr, seg_ent, ent_ptr, peer_dict
+        self.heavy_bound = (int(heavy_bound[0]), int(heavy_bound[1]))   # (max_chunks, max_nodes)
+        self._c = None
+
+    @staticmethod
+    def implicit(node_b, node_e, ent_ptr, ent_adj, peer_frontier, heavy_per_query):
+        """Segments = nodes (node_b[i], node_e[i]); edges pulled from the CSR row of node_e[i] and
+        filtered / ranked through `peer_frontier`'s dictionary."""
+        n_query = peer_frontier.n_query
+        return Segments(1, node_b.shape[0], node_b, ent_adj, n_ent=peer_frontier.n_ent, seg_ent=node_e,
+                        ent_ptr=ent_ptr, peer_dict=peer_frontier.dict,
+                        heavy_bound=(heavy_per_query[0] * n_query, heavy_per_query[1] * n_query))
+
+    @staticmethod
+    def explicit(seg_index, peer_index, rel, query, n_seg):
+        """Group an arbitrary edge list by `seg_index` (stable, so the in-segment order is the
+        caller's edge order).  All arguments are int64 cuda tensors of length E."""
+        order = torch.sort(seg_index, stable=True)[1]
+        deg = torch.bincount(seg_index, minlength=n_seg)
+        seg_ptr = torch.zeros(n_seg + 1, dtype=torch.int64, device=seg_index.device)
+        seg_ptr[1:] = torch.cumsum(deg, 0)
+        adj = torch.stack([peer_index[order], rel[order]], dim=1).to(torch.int32).contiguous()
+        seg_query = torch.zeros(n_seg, dtype=torch.int32, device=seg_index.device)
+        seg_query[seg_index] = query.to(torch.int32)
+        ck = _lib.RG_HEAVY_CHUNK
+        if deg.numel():
+            bound = (int(((deg - 1).clamp_(min=0) // ck).sum()), int((deg > ck).sum()))
+        else:
+            bound = (0, 0)
+        return Segments(0, n_seg, seg_query, adj, seg_ptr=seg_ptr.to(torch.int32).contiguous(), heavy_bound=bound)
+
+    def c_struct(self):
+        if self._c is None:
+            self._c = _lib.RgSegments(self.mode, self.n_ent, self.n_seg, self.seg_query.data_ptr(),
+                                      self.seg_ptr.data_ptr() if self.seg_ptr is not None else None,
+                                      self.adj.data_ptr(),
+                                      self.seg_ent.data_ptr() if self.seg_ent is not None else None,
+                                      self.ent_ptr.data_ptr() if self.ent_ptr is not None else None,
+                                      self.peer_dict.data_ptr() if self.peer_dict is not None else None)
+        return self._c
+
+
+class _Heavy(object):
+    """Queue + partial rows for segments longer than RG_HEAVY_CHUNK slots (allocated per call)."""
+
+    def __init__(self, bound, row_floats, device):
+        self.max_chunks, self.max_nodes = bound
+        self.struct = None
+        if self.max_chunks > 0 and self.max_nodes > 0:
+            i32 = lambda n: torch.empty(n, dtype=torch.int32, device=device)
+            self.counters = torch.zeros(4, dtype=torch.int32, device=device)
+            self.bufs = [i32(self.max_chunks), i32(self.max_chunks), i32(self.max_nodes), i32(self.max_nodes),
+                         i32(self.max_nodes)]
+            self.partial = torch.empty((self.max_chunks, row_floats), dtype=torch.float32, device=device)
+            self.struct = _lib.RgHeavy(self.max_chunks, self.max_nodes, self.counters.data_ptr(),
+                                       *[b.data_ptr() for b in self.bufs], self.partial.data_ptr())
+
+    def ref(self):
+        return C.byref(self.struct) if self.struct is not None else None
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def edge_agg_forward(fwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha):
+    """Raw launcher (no autograd): returns agg [n_seg, D]."""
+    _lib.require_cuda(rela, ar8, aq8, w8, b_alpha, hidden, as8)
+    d = rela.shape[1]
+    agg = torch.empty((fwd_seg.n_seg, d), dtype=torch.float32, device=rela.device)
+    heavy = _Heavy(fwd_seg.heavy_bound, d, rela.device)
+    check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8), ptr(aq8),
+                              ptr(w8), ptr(b_alpha), ptr(agg), heavy.ref(), stream_ptr()))
+    return agg
+
+
+def edge_agg_backward(bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, n_query):
+    """Raw launcher: returns (g_hidden | None, g_as8 | None, g_rela, g_ar8, g_aq8, g_w8, g_b)."""
+    d = rela.shape[1]
+    n_in = bwd_seg.n_seg
+    dev = rela.device
+    g_hidden = torch.empty((n_in, d), dtype=torch.float32, device=dev) if hidden is not None else None
+    node_small = torch.empty((n_in, 24), dtype=torch.float32, device=dev)
+    g_rela = torch.zeros_like(rela)
+    g_ar8 = torch.zeros_like(ar8)
+    heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
+    check(lib.rg_edge_agg_bwd(C.byref(bwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8), ptr(aq8),
+                              ptr(w8), ptr(b_alpha), ptr(g_agg), ptr(g_hidden), ptr(node_small), ptr(g_rela),
+                              ptr(g_ar8), heavy.ref(), stream_ptr()))
+    g_as8 = node_small[:, :8]
+    g_aq8 = torch.zeros((n_query, 8), dtype=torch.float32, device=dev)
+    g_aq8.index_add_(0, bwd_seg.seg_query.long(), g_as8)
+    g_w8 = node_small[:, 8:16].sum(0)
+    g_b = node_small[:, 16].sum().reshape(1)
+    return g_hidden, (g_as8.contiguous() if hidden is not None else None), g_rela, g_ar8, g_aq8, g_w8, g_b
+
+
+class EdgeAggregate(torch.autograd.Function):
+    """agg[s] = sum_{edges e into s} alpha_e * (hidden[p_e] + rela[r_e]),
+    alpha_e = sigmoid(b_alpha + sum_k w8[k] relu(as8[p_e][k] + ar8[r_e][k] + aq8[q_e][k]))."""
+
+    @staticmethod
+    def forward(ctx, hidden, as8, rela, ar8, aq8, w8, b_alpha, fwd_seg, bwd_seg):
+        hidden, as8, rela, ar8, aq8, w8, b_alpha = (_f32c(t) for t in (hidden, as8, rela, ar8, aq8, w8, b_alpha))
+        agg = edge_agg_forward(fwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha)
+        ctx.has_hidden = hidden is not None
+        saved = [rela, ar8, aq8, w8, b_alpha] + ([hidden, as8] if ctx.has_hidden else [])
+        ctx.save_for_backward(*saved)
+        ctx.bwd_seg = bwd_seg
+        return agg
+
+    @staticmethod
+    def backward(ctx, g_agg):
+        saved = ctx.saved_tensors
+        rela, ar8, aq8, w8, b_alpha = saved[:5]
+        hidden, as8 = (saved[5], saved[6]) if ctx.has_hidden else (None, None)
+        g_agg = g_agg.to(torch.float32).contiguous()
+        g_hidden, g_as8, g_rela, g_ar8, g_aq8, g_w8, g_b = edge_agg_backward(
+            ctx.bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, aq8.shape[0])
+        return g_hidden, g_as8, g_rela, g_ar8, g_aq8, g_w8, g_b, None, None
+
+
+def edge_aggregate(hidden, as8, rela, ar8, aq8, w8, b_alpha, fwd_seg, bwd_seg):
+    return EdgeAggregate.apply(hidden, as8, rela, ar8, aq8, w8, b_alpha, fwd_seg, bwd_seg)

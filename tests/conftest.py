@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def tiny_dir(tmp_path_factory):
+    from redgnn_b200 import synth
+    return synth.write_transductive(str(tmp_path_factory.mktemp("tiny")), "tiny", seed=3)
+
+
+@pytest.fixture(scope="session")
+def hub_dir(tmp_path_factory):
+    """Small KG with strong hubs (degree >> RG_HEAVY_CHUNK) to exercise the heavy-segment queue."""
+    from redgnn_b200 import synth
+    return synth.write_transductive(str(tmp_path_factory.mktemp("hub")), seed=5,
+                                    override=(500, 5, 12000, 100, 100, 1.6, 1.6, 3))
+
+
+@pytest.fixture(scope="session")
+def induc_dir(tmp_path_factory):
+    from redgnn_b200 import synth
+    return synth.write_inductive(os.path.join(str(tmp_path_factory.mktemp("induc")), "syn_v1"), seed=11)

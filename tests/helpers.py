@@ -1,0 +1,75 @@
+"""Shared test helpers (the oracle is imported here and only here / in tests)."""
+import hashlib
+import os
+
+import numpy as np
+import torch
+
+from oracle import redgnn_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def sha(t):
+    if isinstance(t, torch.Tensor):
+        t = t.detach().cpu().contiguous().numpy()
+    return hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
+
+
+def golden_state_dict(fx):
+    return {k[3:]: torch.from_numpy(fx[k].copy()) for k in fx.files if k.startswith("sd.")}
+
+
+def family_graphs(fx):
+    """(train graph, test graph) oracle Graphs rebuilt from the family fixture
+    (transductive/load_data.py:43-44)."""
+    n_ent, n_rel = int(fx["n_ent"]), int(fx["n_rel"])
+    fact = fx["fact_triple"].astype(np.int64).tolist()
+    train = fx["train_triple"].astype(np.int64).tolist()
+    g_train = O.Graph(O.add_inverse_block(fact, n_rel), n_ent, n_rel)
+    g_test = O.Graph(O.add_inverse_block(fact, n_rel) + O.add_inverse_block(train, n_rel), n_ent, n_rel)
+    return g_train, g_test
+
+
+def graph_triples(g):
+    """triples (without the self-loop block) of an oracle Graph as int64 [T,3]."""
+    return g.KG[:-g.n_ent].astype(np.int64)
+
+
+def device_graph(g, device="cuda"):
+    from redgnn_b200 import DeviceGraph
+    return DeviceGraph(graph_triples(g), g.n_ent, g.n_rel, device)
+
+
+def assert_expansion_equal(got, want, tag=""):
+    names = ("tail_nodes", "edges", "old_nodes_new_idx")
+    for name, a, b in zip(names, got, want):
+        a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+        b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+        assert a.dtype == np.int64, "%s %s dtype %s" % (tag, name, a.dtype)
+        assert a.shape == b.shape, "%s %s shape %s vs %s" % (tag, name, a.shape, b.shape)
+        if not np.array_equal(a, b):
+            bad = np.argwhere(a != b)
+            same_set = name == "edges" and np.array_equal(np.sort(a.view([("", a.dtype)] * a.shape[1]), axis=0),
+                                                          np.sort(b.view([("", b.dtype)] * b.shape[1]), axis=0))
+            raise AssertionError("%s %s differs at %d entries; first %s got %s want %s; same multiset of rows: %s"
+                                 % (tag, name, len(bad), bad[0], a[tuple(bad[0])], b[tuple(bad[0])], same_set))
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def assert_close(a, b, rtol=1e-4, tag=""):
+    """max |a-b| <= rtol * max|b|  (north_star: scores within 1e-4 relative in fp32)."""
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, "%s shape %s vs %s" % (tag, tuple(a.shape), tuple(b.shape))
+    scale = b.abs().max().clamp_min(1e-30)
+    err = (a - b).abs().max()
+    assert err <= rtol * scale, "%s: max abs err %.3e vs scale %.3e (rel %.3e > %.1e)" % (
+        tag, err.item(), scale.item(), (err / scale).item(), rtol)
