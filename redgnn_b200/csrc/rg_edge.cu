@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(kBlock) k_edge_fwd(rg_segments S, const float 
     if (seg >= S.n_seg) return;
     SegRange r = seg_range<IMPLICIT>(S, seg);
     int hi = r.hi;
-    if (r.hi - r.lo > RG_HEAVY_CHUNK) {
-        if (has_heavy) enqueue_heavy(H, seg, r.hi - r.lo, lane);
+    if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all
+        enqueue_heavy(H, seg, r.hi - r.lo, lane);
         hi = r.lo + RG_HEAVY_CHUNK;
     }
     float4 acc[D / 16];
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
     if (seg >= S.n_seg) return;
     SegRange r = seg_range<IMPLICIT>(S, seg);
     int hi = r.hi;
-    if (r.hi - r.lo > RG_HEAVY_CHUNK) {
-        if (has_heavy) enqueue_heavy(H, seg, r.hi - r.lo, lane);
+    if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all
+        enqueue_heavy(H, seg, r.hi - r.lo, lane);
         hi = r.lo + RG_HEAVY_CHUNK;
     }
     float4 G[D / 16];

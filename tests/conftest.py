@@ -23,7 +23,7 @@ def hub_dir(tmp_path_factory):
     """Small KG with strong hubs (degree >> RG_HEAVY_CHUNK) to exercise the heavy-segment queue."""
     from redgnn_b200 import synth
     return synth.write_transductive(str(tmp_path_factory.mktemp("hub")), seed=5,
-                                    override=(500, 5, 12000, 100, 100, 1.6, 1.6, 3))
+                                    override=(2000, 4, 30000, 100, 100, 1.2, 1.2, 3))
 
 
 @pytest.fixture(scope="session")

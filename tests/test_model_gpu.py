@@ -1,0 +1,168 @@
+"""GPU parity of the whole path behind RED_GNN_trans / RED_GNN_induc.forward: per-entity scores
+within 1e-4 relative (fp32), unvisited entities exactly 0, parameter gradients of the reference
+training loss within 1e-4, filtered ranks / MRR / Hits identical to 3 decimals."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import redgnn_oracle as O
+from helpers import golden, golden_state_dict, assert_close
+from redgnn_b200.synth import Options
+
+pytestmark = pytest.mark.gpu
+
+
+def write_family_dir(tmp_path, fx):
+    """Rebuild a dataset directory in the reference's text layout from the family fixture."""
+    d = tmp_path / "family"
+    d.mkdir()
+    n_ent, n_rel = int(fx["n_ent"]), int(fx["n_rel"])
+    (d / "entities.txt").write_text("".join("e%d\n" % i for i in range(n_ent)))
+    (d / "relations.txt").write_text("".join("r%d\n" % i for i in range(n_rel)))
+    dump = lambda tri: "".join("e%d r%d e%d\n" % tuple(t) for t in tri.tolist())
+    (d / "facts.txt").write_text(dump(fx["fact_triple"]))
+    (d / "train.txt").write_text(dump(fx["train_triple"]))
+    (d / "valid.txt").write_text("e0 r0 e1\n")
+    (d / "test.txt").write_text("e0 r0 e1\n")
+    return str(d)
+
+
+def test_golden_family_scores_ranks_grads(tmp_path):
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    fx = golden("family")
+    L = TransductiveLoader(write_family_dir(tmp_path, fx))
+    opts = Options(hidden_dim=48, attn_dim=5, n_layer=3, dropout=0.29, act="relu", n_rel=L.n_rel)
+    model = RED_GNN_trans(opts, L).cuda()
+    model.load_state_dict(golden_state_dict(fx))          # reference parameter names load unchanged
+    model.eval()
+    scores = model(fx["eval_subs"], fx["eval_rels"], mode="test")
+    want = torch.from_numpy(fx["eval_scores"])
+    assert_close(scores, want, 1e-4, "family scores")
+    assert torch.equal(scores.cpu() == 0, want == 0), "visited / unvisited entity sets differ"
+    ranks = O.cal_ranks(scores.detach().cpu().numpy(), fx["eval_objs"].astype(np.float64),
+                        fx["eval_filters"].astype(np.float64))
+    assert np.array_equal(np.array(ranks), fx["eval_ranks"])
+    for a, b in zip(O.cal_performance(ranks), O.cal_performance(fx["eval_ranks"])):
+        assert round(a, 3) == round(b, 3)
+    tri = fx["train_triples"]
+    model.zero_grad()
+    out = model(tri[:, 0], tri[:, 1])                     # mode='train' graph, eval() => no dropout
+    pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
+    mx = out.max(1, keepdim=True)[0]
+    loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1)))
+    loss.backward()
+    assert abs(loss.item() - float(fx["train_loss"])) <= 1e-4 * abs(float(fx["train_loss"]))
+    for k, p in model.named_parameters():
+        assert_close(p.grad, torch.from_numpy(fx["train_grad." + k]), 1e-4, "family grad " + k)
+
+
+@pytest.mark.parametrize("act,d,a,n_layer", [("relu", 48, 5, 3), ("tanh", 32, 3, 4), ("idd", 64, 5, 2)])
+def test_transductive_model_vs_oracle(tiny_dir, act, d, a, n_layer):
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    L, D = TransductiveLoader(tiny_dir), O.TransductiveData(tiny_dir)
+    sd = O.init_state_dict(n_layer, d, a, D.n_rel, seed=7)
+    opts = Options(hidden_dim=d, attn_dim=a, n_layer=n_layer, dropout=0.1, act=act, n_rel=L.n_rel)
+    model = RED_GNN_trans(opts, L).cuda()
+    model.load_state_dict(sd)
+    model.eval()
+    subs, rels, objs = L.get_batch(np.arange(40), data="test")
+    for mode in ("train", "test"):
+        got = model(subs, rels, mode=mode)
+        want = O.model_forward(sd, D.graph_for(mode), subs, rels, n_layer, act)
+        assert_close(got, want, 1e-4, "scores " + mode)
+        assert torch.equal(got.cpu() == 0, want == 0)
+    # gradients of the training loss (base_model.py:58-60)
+    tri = L.get_batch(np.arange(10))
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.train_loss(O.model_forward(sd_g, D.graph, tri[:, 0], tri[:, 1], n_layer, act), tri[:, 2]).backward()
+    out = model(tri[:, 0], tri[:, 1])
+    pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
+    mx = out.max(1, keepdim=True)[0]
+    model.zero_grad()
+    torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1))).backward()
+    for k, p in model.named_parameters():
+        assert_close(p.grad, sd_g[k].grad, 1e-4, "grad " + k)
+    # a second identical forward is bit-identical (no atomics in the forward path)
+    assert torch.equal(model(subs, rels, mode="test"), model(subs, rels, mode="test"))
+
+
+def test_hub_model_vs_oracle(hub_dir):
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    L, D = TransductiveLoader(hub_dir), O.TransductiveData(hub_dir)
+    sd = O.init_state_dict(3, 48, 5, D.n_rel, seed=9)
+    model = RED_GNN_trans(Options(n_rel=L.n_rel), L).cuda()
+    model.load_state_dict(sd)
+    model.eval()
+    subs, rels, _ = L.get_batch(np.arange(8), data="valid")
+    got = model(subs, rels, mode="valid")
+    want = O.model_forward(sd, D.test_graph, subs, rels, 3, "relu")
+    assert_close(got, want, 1e-4, "hub scores")
+    tri = L.get_batch(np.arange(4))
+    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.train_loss(O.model_forward(sd_g, D.graph, tri[:, 0], tri[:, 1], 3, "relu"), tri[:, 2]).backward()
+    out = model(tri[:, 0], tri[:, 1])
+    pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
+    mx = out.max(1, keepdim=True)[0]
+    model.zero_grad()
+    torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1))).backward()
+    for k, p in model.named_parameters():
+        assert_close(p.grad, sd_g[k].grad, 1e-4, "hub grad " + k)
+
+
+def test_inductive_model_vs_oracle_and_golden(induc_dir):
+    from redgnn_b200 import InductiveLoader, RED_GNN_induc
+    L, D = InductiveLoader(induc_dir), O.InductiveData(induc_dir)
+    sd = O.init_state_dict(3, 48, 5, D.n_rel, seed=5)
+    model = RED_GNN_induc(Options(n_rel=L.n_rel), L).cuda()
+    model.load_state_dict(sd)
+    model.eval()
+    subs, rels, _ = L.get_batch(np.arange(15), data="valid")
+    got = model(subs, rels)
+    assert got.shape == (15, L.n_ent)
+    assert_close(got, O.model_forward(sd, D.tra_graph, subs, rels, 3, "relu"), 1e-4, "transductive mode")
+    subs, rels, _ = L.get_batch(np.arange(15), data="test")
+    got = model(subs, rels, "inductive")
+    assert got.shape == (15, L.n_ent_ind)
+    want = O.model_forward(sd, D.ind_graph, subs, rels, 3, "relu", n_ent_out=D.n_ent_ind)
+    assert_close(got, want, 1e-4, "inductive mode")
+
+
+def test_golden_fb237_v2_scores(tmp_path):
+    """Scores the live reference produced for fb237_v2 (inductive mode) vs the CUDA path, with the
+    graph rebuilt from the fixture through DeviceGraph directly."""
+    from redgnn_b200 import RED_GNN_induc, DeviceGraph
+
+    fx = golden("fb237_v2")
+
+    class FixtureLoader(object):
+        n_ent, n_ent_ind, n_rel = int(fx["n_ent"]), int(fx["n_ent_ind"]), int(fx["n_rel"])
+
+        def __init__(self):
+            self.g = {"transductive": DeviceGraph(fx["tra_triples"].astype(np.int64), self.n_ent, self.n_rel, "cuda"),
+                      "inductive": DeviceGraph(fx["ind_triples"].astype(np.int64), self.n_ent_ind, self.n_rel, "cuda")}
+
+        def graph_for(self, mode, device=None):
+            return self.g["transductive" if mode == "transductive" else "inductive"]
+
+        def n_ent_for(self, mode):
+            return self.n_ent if mode == "transductive" else self.n_ent_ind
+
+    L = FixtureLoader()
+    model = RED_GNN_induc(Options(n_rel=L.n_rel, dropout=0.3), L).cuda()
+    model.load_state_dict(golden_state_dict(fx))
+    model.eval()
+    scores = model(fx["eval_subs"], fx["eval_rels"], "inductive")
+    want = torch.from_numpy(fx["eval_scores"])
+    assert_close(scores, want, 1e-4, "fb237_v2 scores")
+    assert torch.equal(scores.cpu() == 0, want == 0)
+    ranks = O.cal_ranks(scores.detach().cpu().numpy(), fx["eval_objs"].astype(np.float64),
+                        fx["eval_filters"].astype(np.float64))
+    assert np.array_equal(np.array(ranks), fx["eval_ranks"])
+    tri = fx["train_triples"]
+    out = model(tri[:, 0], tri[:, 1])
+    pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
+    mx = out.max(1, keepdim=True)[0]
+    model.zero_grad()
+    torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1))).backward()
+    for k, p in model.named_parameters():
+        assert_close(p.grad, torch.from_numpy(fx["train_grad." + k]), 1e-4, "fb237_v2 grad " + k)
