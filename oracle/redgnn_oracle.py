@@ -192,16 +192,17 @@ def model_forward(sd, graph, subs, rels, n_layer, act, n_ent_out=None, dropout_m
     """
     n = len(subs)
     d = sd["W_final.weight"].shape[1]
+    dt = sd["W_final.weight"].dtype          # fp32 like the reference; fp64 for error yardsticks in tests
     q_sub = torch.as_tensor(np.asarray(subs), dtype=torch.long)
     q_rel = torch.as_tensor(np.asarray(rels), dtype=torch.long)
-    h0 = torch.zeros(n, d)
+    h0 = torch.zeros(n, d, dtype=dt)
     nodes = torch.stack([torch.arange(n), q_sub], dim=1)                 # :73
-    hidden = torch.zeros(n, d)
+    hidden = torch.zeros(n, d, dtype=dt)
     trace = []
     for i in range(n_layer):
         nodes, edges, remap = get_neighbors(graph, nodes.numpy())        # :78
         hidden = gnn_layer_forward(sd, i, q_rel, hidden, edges, nodes.shape[0], act)   # :80
-        h0 = torch.zeros(nodes.shape[0], d).index_copy_(0, remap, h0)    # :81
+        h0 = torch.zeros(nodes.shape[0], d, dtype=dt).index_copy_(0, remap, h0)    # :81
         if dropout_masks is not None:
             hidden = hidden * dropout_masks[i]                           # :82
         hidden = gru_step(sd, hidden, h0)                                # :83
@@ -210,7 +211,7 @@ def model_forward(sd, graph, subs, rels, n_layer, act, n_ent_out=None, dropout_m
             trace.append((nodes, edges, remap))
     scores = (hidden @ sd["W_final.weight"].t()).squeeze(-1)             # :86
     n_ent_out = graph.n_ent if n_ent_out is None else n_ent_out
-    scores_all = torch.zeros(n, n_ent_out)                               # :87
+    scores_all = torch.zeros(n, n_ent_out, dtype=dt)                     # :87
     scores_all[nodes[:, 0], nodes[:, 1]] = scores                        # :88
     if return_trace:
         return scores_all, trace

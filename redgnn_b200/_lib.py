@@ -85,6 +85,44 @@ class RgError(RuntimeError):
     pass
 
 
+class Stats(object):
+    """Launch bookkeeping for bench.py: how many of this library's kernels were launched, and
+    (when `timing` is a list) CUDA-event pairs around the named kernels on the launching stream."""
+    launches = 0
+    timing = None
+
+    @classmethod
+    def timed(cls, name, meta=None):
+        return _Timed(name, meta) if cls.timing is not None else _NULL
+
+
+class _Null(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NULL = _Null()
+
+
+class _Timed(object):
+    def __init__(self, name, meta):
+        import torch
+        self.name, self.meta = name, meta
+        self.t0, self.t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        self.t0.record()
+        return self
+
+    def __exit__(self, *a):
+        self.t1.record()
+        Stats.timing.append((self.name, self.meta, self.t0, self.t1))
+        return False
+
+
 def check(rc):
     if rc != 0:
         raise RgError("libredgnn_b200: %s (status %d)" % (lib.rg_strerror(rc).decode(), rc))

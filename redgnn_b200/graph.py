@@ -80,6 +80,7 @@ class DeviceGraph(object):
         ws = self.workspace(n_query)
         check(lib.rg_frontier_from_nodes(ptr(nodes64), nodes64.shape[0], C.byref(fr.c_struct()), ptr(fr.counts),
                                          ptr(ws), ws.numel(), stream_ptr()))
+        _lib.Stats.launches += 4      # k_set_nodes + dict reduce / scan / apply
         return fr
 
     def step(self, fr_in):
@@ -89,6 +90,7 @@ class DeviceGraph(object):
         ws = self.workspace(fr_in.n_query)
         check(lib.rg_frontier_step(C.byref(self.c_struct()), C.byref(fr_in.c_struct()), C.byref(fr_out.c_struct()),
                                    ptr(fr_out.counts), ptr(ws), ws.numel(), stream_ptr()))
+        _lib.Stats.launches += 6      # fact_count, scan, transpose, dict reduce / scan / apply
         return fr_out
 
     def emit_edges(self, fr_in, fr_out, n_edges):
@@ -96,6 +98,7 @@ class DeviceGraph(object):
         ws = self.workspace(fr_in.n_query)
         check(lib.rg_edges_emit(C.byref(self.c_struct()), C.byref(fr_in.c_struct()), C.byref(fr_out.c_struct()),
                                 ptr(ws), ws.numel(), n_edges, ptr(edges), stream_ptr()))
+        _lib.Stats.launches += 1
         return edges
 
     def get_neighbors(self, nodes, n_query=None):
@@ -154,16 +157,19 @@ class Frontier(object):
     def nodes64(self, n_nodes):
         out = torch.empty((n_nodes, 2), dtype=torch.int64, device=self.emask.device)
         check(lib.rg_frontier_nodes(C.byref(self.c_struct()), ptr(out), None, None, stream_ptr()))
+        _lib.Stats.launches += 1
         return out
 
     def nodes32(self, n_nodes):
         b = torch.empty(n_nodes, dtype=torch.int32, device=self.emask.device)
         e = torch.empty(n_nodes, dtype=torch.int32, device=self.emask.device)
         check(lib.rg_frontier_nodes(C.byref(self.c_struct()), None, ptr(b), ptr(e), stream_ptr()))
+        _lib.Stats.launches += 1
         return b, e
 
     def remap_to(self, fr_out, n_nodes):
         out = torch.empty(n_nodes, dtype=torch.int64, device=self.emask.device)
         check(lib.rg_frontier_remap(C.byref(self.c_struct()), C.byref(fr_out.c_struct()), ptr(out), None,
                                     stream_ptr()))
+        _lib.Stats.launches += 1
         return out

@@ -52,6 +52,10 @@ class GNNLayer(torch.nn.Module):
         as8 = _pad8(self.Ws_attn(hidden)) if hidden is not None else None
         ar8 = _pad8(self.Wr_attn(rela))
         aq8 = _pad8(self.Wqr_attn(rela[q_rel]))
+        if hidden is None and torch.is_grad_enabled():
+            # the reference multiplies Ws_attn by an all-zero hidden at layer 0: its gradient is an
+            # explicit zero (not None), which Adam's weight decay still acts on -- keep that
+            aq8 = aq8 + 0.0 * self.Ws_attn.weight.sum()
         w8 = _pad8(self.w_alpha.weight).reshape(8)
         agg = edge_aggregate(hidden, as8, rela, ar8, aq8, w8, self.w_alpha.bias, fwd_seg, bwd_seg)
         return self.act(self.W_h(agg))
@@ -99,14 +103,20 @@ class RedGNN(torch.nn.Module):
         n = torch.tanh(i_n + r * h_n)
         return (1.0 - z) * n + z * h
 
+    @staticmethod
+    def _to_device(x, dev):
+        """numpy / list (the reference's calling convention) or a tensor already on the device."""
+        if isinstance(x, torch.Tensor):
+            return x.to(device=dev, dtype=torch.int64, non_blocking=True)
+        return torch.as_tensor(np.asarray(x), dtype=torch.int64).to(dev, non_blocking=True)
+
     def _run(self, subs, rels, graph, n_ent_out):
         dev = self.W_final.weight.device
         if dev.type != 'cuda':
             raise _lib.RgError("redgnn_b200: the model must live on a CUDA device (call .cuda()); no CPU path exists")
         n = len(subs)
         d = self.hidden_dim
-        q_sub = torch.as_tensor(np.asarray(subs), dtype=torch.int64).to(dev, non_blocking=True)
-        q_rel = torch.as_tensor(np.asarray(rels), dtype=torch.int64).to(dev, non_blocking=True)
+        q_sub, q_rel = self._to_device(subs, dev), self._to_device(rels, dev)
         need_grad = torch.is_grad_enabled()
 
         batch = torch.arange(n, device=dev)
@@ -126,6 +136,9 @@ class RedGNN(torch.nn.Module):
             fwd_seg = Segments.implicit(nb, ne, graph.in_ptr, graph.in_adj, fr, graph.heavy_in)
             bwd_seg = Segments.implicit(node_b, node_e, graph.out_ptr, graph.out_adj, fr_next, graph.heavy_out) \
                 if need_grad else None
+            fwd_seg.n_edges = n_edges
+            if bwd_seg is not None:
+                bwd_seg.n_edges = n_edges
             hidden = self.gnn_layers[i].propagate(q_rel, hidden, fwd_seg, bwd_seg)
             h0 = torch.zeros((n_next, d), device=dev).index_copy_(0, remap, h0)
             hidden = self.dropout(hidden)

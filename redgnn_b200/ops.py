@@ -21,6 +21,7 @@ class Segments(object):
         self.seg_query, self.adj = seg_query, adj
         self.seg_ptr, self.seg_ent, self.ent_ptr, self.peer_dict = seg_ptr, seg_ent, ent_ptr, peer_dict
         self.heavy_bound = (int(heavy_bound[0]), int(heavy_bound[1]))   # (max_chunks, max_nodes)
+        self.n_edges = int(adj.shape[0]) if mode == 0 else None       # implicit: set by the caller if known
         self._c = None
 
     @staticmethod
@@ -90,8 +91,10 @@ def edge_agg_forward(fwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha):
     d = rela.shape[1]
     agg = torch.empty((fwd_seg.n_seg, d), dtype=torch.float32, device=rela.device)
     heavy = _Heavy(fwd_seg.heavy_bound, d, rela.device)
-    check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8), ptr(aq8),
-                              ptr(w8), ptr(b_alpha), ptr(agg), heavy.ref(), stream_ptr()))
+    with _lib.Stats.timed("edge_fwd", (fwd_seg.n_seg, d, hidden is not None, fwd_seg.n_edges)):
+        check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
+                                  ptr(aq8), ptr(w8), ptr(b_alpha), ptr(agg), heavy.ref(), stream_ptr()))
+    _lib.Stats.launches += 3 if heavy.struct is not None else 1
     return agg
 
 
@@ -105,9 +108,11 @@ def edge_agg_backward(bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, 
     g_rela = torch.zeros_like(rela)
     g_ar8 = torch.zeros_like(ar8)
     heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
-    check(lib.rg_edge_agg_bwd(C.byref(bwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8), ptr(aq8),
-                              ptr(w8), ptr(b_alpha), ptr(g_agg), ptr(g_hidden), ptr(node_small), ptr(g_rela),
-                              ptr(g_ar8), heavy.ref(), stream_ptr()))
+    with _lib.Stats.timed("edge_bwd", (n_in, d, hidden is not None, bwd_seg.n_edges)):
+        check(lib.rg_edge_agg_bwd(C.byref(bwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
+                                  ptr(aq8), ptr(w8), ptr(b_alpha), ptr(g_agg), ptr(g_hidden), ptr(node_small),
+                                  ptr(g_rela), ptr(g_ar8), heavy.ref(), stream_ptr()))
+    _lib.Stats.launches += 3 if heavy.struct is not None else 1
     g_as8 = node_small[:, :8]
     g_aq8 = torch.zeros((n_query, 8), dtype=torch.float32, device=dev)
     g_aq8.index_add_(0, bwd_seg.seg_query.long(), g_as8)

@@ -73,3 +73,20 @@ def assert_close(a, b, rtol=1e-4, tag=""):
     err = (a - b).abs().max()
     assert err <= rtol * scale, "%s: max abs err %.3e vs scale %.3e (rel %.3e > %.1e)" % (
         tag, err.item(), scale.item(), (err / scale).item(), rtol)
+
+
+def assert_grad_close(mine, ref32, ref64, rtol=1e-4, tag=""):
+    """Gradient parity.  Pass if max|mine - ref64| <= rtol * max|ref64|, or -- for sums with heavy
+    cancellation, where fp32 itself cannot hold rtol -- if the error is within 4x the error the
+    reference's own fp32 arithmetic (ref32) makes against the fp64 evaluation of the same formula."""
+    m, r32, r64 = (t.detach().cpu().double() for t in (mine, ref32, ref64))
+    assert m.shape == r64.shape, "%s shape %s vs %s" % (tag, tuple(m.shape), tuple(r64.shape))
+    scale = r64.abs().max().clamp_min(1e-30)
+    err, err_ref = (m - r64).abs().max(), (r32 - r64).abs().max()
+    assert err <= rtol * scale or err <= 4 * err_ref, \
+        "%s: max abs err %.3e (fp32 reference itself: %.3e) vs scale %.3e (rel %.3e > %.1e)" % (
+            tag, err.item(), err_ref.item(), scale.item(), (err / scale).item(), rtol)
+
+
+def to64(sd):
+    return {k: v.double() for k, v in sd.items()}

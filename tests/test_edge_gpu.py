@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import redgnn_oracle as O
-from helpers import device_graph, assert_close
+from helpers import device_graph, assert_close, assert_grad_close, to64
 
 pytestmark = pytest.mark.gpu
 ACT = {"relu": torch.relu, "tanh": torch.tanh, "idd": lambda x: x}
@@ -19,11 +19,25 @@ def make_layer(d, a, n_rel, act, seed):
     return layer.cuda(), sd
 
 
-def oracle_layer(sd, q_rel, hidden, edges, n_node, act):
-    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    hidden = hidden.clone().requires_grad_(True)
-    out = O.gnn_layer_forward(sd, 0, q_rel, hidden, edges, n_node, act)
-    return out, sd, hidden
+def oracle_layer(sd, q_rel, hidden, edges, n_node, act, w=None):
+    """fp32 oracle (and, given the output cotangent w, its gradients in fp32 and fp64)."""
+    res = []
+    for conv in ((lambda t: t.clone()), (lambda t: t.double())):
+        sdc = {k: conv(v).requires_grad_(True) for k, v in sd.items()}
+        hid = conv(hidden).requires_grad_(True)
+        out = O.gnn_layer_forward(sdc, 0, q_rel, hid, edges, n_node, act)
+        if w is not None:
+            (out * conv(w)).sum().backward()
+        res.append((out, sdc, hid))
+    return res
+
+
+def check_layer_grads(layer, hid_c, res, tag):
+    (_, sd32, hid32), (_, sd64, hid64) = res
+    assert_grad_close(hid_c.grad, hid32.grad, hid64.grad, 1e-4, tag + " grad hidden")
+    for k, p in layer.named_parameters():
+        key = "gnn_layers.0." + k
+        assert_grad_close(p.grad, sd32[key].grad, sd64[key].grad, 1e-4, tag + " grad " + k)
 
 
 @pytest.mark.parametrize("d,a,act", [(48, 5, "relu"), (32, 3, "tanh"), (64, 5, "idd"), (16, 8, "relu")])
@@ -40,16 +54,14 @@ def test_explicit_layer_forward_backward(tiny_dir, d, a, act):
     hidden = torch.randn(nodes1.shape[0], d)
     q_rel = torch.as_tensor(rels)
     layer, sd = make_layer(d, a, D.n_rel, act, seed=1)
-    want, sd_g, hid_g = oracle_layer(sd, q_rel, hidden, edges, nodes2.shape[0], act)
+    torch.manual_seed(3)
+    w = torch.randn(nodes2.shape[0], d)
+    res = oracle_layer(sd, q_rel, hidden, edges, nodes2.shape[0], act, w)
     hid_c = hidden.cuda().requires_grad_(True)
     got = layer(torch.as_tensor(subs).cuda(), q_rel.cuda(), hid_c, edges.cuda(), nodes2.shape[0], remap.cuda())
-    assert_close(got, want, 1e-4, "forward")
-    w = torch.randn_like(want)
-    (want * w).sum().backward()
+    assert_close(got, res[0][0], 1e-4, "forward")
     (got * w.cuda()).sum().backward()
-    assert_close(hid_c.grad, hid_g.grad, 1e-4, "grad hidden")
-    for k, p in layer.named_parameters():
-        assert_close(p.grad, sd_g["gnn_layers.0." + k].grad, 1e-4, "grad " + k)
+    check_layer_grads(layer, hid_c, res, "explicit")
 
 
 def test_explicit_layer_empty_segments_and_zero_hidden(tiny_dir):
@@ -82,18 +94,15 @@ def test_heavy_segments_explicit_and_deterministic(hub_dir):
     torch.manual_seed(1)
     hidden = torch.randn(nodes1.shape[0], 48)
     q_rel = torch.arange(n) % (2 * D.n_rel)
-    want, sd_g, hid_g = oracle_layer(sd, q_rel, hidden, edges, nodes2.shape[0], "relu")
+    w = torch.randn(nodes2.shape[0], 48)
+    res = oracle_layer(sd, q_rel, hidden, edges, nodes2.shape[0], "relu", w)
     hid_c = hidden.cuda().requires_grad_(True)
     got = layer(None, q_rel.cuda(), hid_c, edges.cuda(), nodes2.shape[0], None)
-    assert_close(got, want, 1e-4, "heavy forward")
+    assert_close(got, res[0][0], 1e-4, "heavy forward")
     got2 = layer(None, q_rel.cuda(), hid_c, edges.cuda(), nodes2.shape[0], None)
     assert torch.equal(got, got2), "forward must be bit-reproducible"
-    w = torch.randn_like(want)
-    (want * w).sum().backward()
     (got * w.cuda()).sum().backward()
-    assert_close(hid_c.grad, hid_g.grad, 1e-4, "heavy grad hidden")
-    for k, p in layer.named_parameters():
-        assert_close(p.grad, sd_g["gnn_layers.0." + k].grad, 1e-4, "heavy grad " + k)
+    check_layer_grads(layer, hid_c, res, "heavy")
 
 
 @pytest.mark.parametrize("fixture,extra_hops", [("tiny_dir", 0), ("hub_dir", 1)])

@@ -6,10 +6,30 @@ import pytest
 import torch
 
 from oracle import redgnn_oracle as O
-from helpers import golden, golden_state_dict, assert_close
+from helpers import golden, golden_state_dict, assert_close, assert_grad_close, to64
 from redgnn_b200.synth import Options
 
 pytestmark = pytest.mark.gpu
+
+
+def oracle_loss_grads(sd, graph, tri, n_layer, act):
+    """Gradients of the reference training loss (base_model.py:58-60) in fp32 and fp64."""
+    out = []
+    for conv in ((lambda t: t.clone()), (lambda t: t.double())):
+        sd_g = {k: conv(v).requires_grad_(True) for k, v in sd.items()}
+        O.train_loss(O.model_forward(sd_g, graph, tri[:, 0], tri[:, 1], n_layer, act), tri[:, 2]).backward()
+        out.append({k: v.grad for k, v in sd_g.items()})
+    return out
+
+
+def cuda_loss_backward(model, tri):
+    out = model(tri[:, 0], tri[:, 1])
+    pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
+    mx = out.max(1, keepdim=True)[0]
+    model.zero_grad()
+    loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1)))
+    loss.backward()
+    return loss
 
 
 def write_family_dir(tmp_path, fx):
@@ -73,15 +93,10 @@ def test_transductive_model_vs_oracle(tiny_dir, act, d, a, n_layer):
         assert torch.equal(got.cpu() == 0, want == 0)
     # gradients of the training loss (base_model.py:58-60)
     tri = L.get_batch(np.arange(10))
-    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    O.train_loss(O.model_forward(sd_g, D.graph, tri[:, 0], tri[:, 1], n_layer, act), tri[:, 2]).backward()
-    out = model(tri[:, 0], tri[:, 1])
-    pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
-    mx = out.max(1, keepdim=True)[0]
-    model.zero_grad()
-    torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1))).backward()
+    g32, g64 = oracle_loss_grads(sd, D.graph, tri, n_layer, act)
+    cuda_loss_backward(model, tri)
     for k, p in model.named_parameters():
-        assert_close(p.grad, sd_g[k].grad, 1e-4, "grad " + k)
+        assert_grad_close(p.grad, g32[k], g64[k], 1e-4, "grad " + k)
     # a second identical forward is bit-identical (no atomics in the forward path)
     assert torch.equal(model(subs, rels, mode="test"), model(subs, rels, mode="test"))
 
@@ -98,15 +113,10 @@ def test_hub_model_vs_oracle(hub_dir):
     want = O.model_forward(sd, D.test_graph, subs, rels, 3, "relu")
     assert_close(got, want, 1e-4, "hub scores")
     tri = L.get_batch(np.arange(4))
-    sd_g = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    O.train_loss(O.model_forward(sd_g, D.graph, tri[:, 0], tri[:, 1], 3, "relu"), tri[:, 2]).backward()
-    out = model(tri[:, 0], tri[:, 1])
-    pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
-    mx = out.max(1, keepdim=True)[0]
-    model.zero_grad()
-    torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1))).backward()
+    g32, g64 = oracle_loss_grads(sd, D.graph, tri, 3, "relu")
+    cuda_loss_backward(model, tri)
     for k, p in model.named_parameters():
-        assert_close(p.grad, sd_g[k].grad, 1e-4, "hub grad " + k)
+        assert_grad_close(p.grad, g32[k], g64[k], 1e-4, "hub grad " + k)
 
 
 def test_inductive_model_vs_oracle_and_golden(induc_dir):
