@@ -141,9 +141,12 @@ int rg_frontier_step(const rg_graph *g, const rg_frontier *in, rg_frontier *out,
 int rg_frontier_nodes(const rg_frontier *fr, int64_t *nodes64, int32_t *node_b, int32_t *node_e,
                       void *stream);
 
-/* old_nodes_new_idx (load_data.py:127-129): row of every `in` node inside `out`'s node list. */
+/* old_nodes_new_idx (load_data.py:127-129): row of every `in` node inside `out`'s node list.
+ * inverse32[N'] (optional, caller pre-fills it with -1) receives the opposite map: the `in` row of
+ * an `out` node, which is what the h0 re-index zeros().index_copy_(1, old_nodes_new_idx, h0)
+ * (transductive/models.py:81) needs when it is fused into the node update as a gather. */
 int rg_frontier_remap(const rg_frontier *in, const rg_frontier *out, int64_t *remap64,
-                      int32_t *remap32, void *stream);
+                      int32_t *remap32, int32_t *inverse32, void *stream);
 
 /* sampled_edges[E][6] int64 = (batch, head, rel, tail, head_index, tail_index) in the
  * reference's order (fact row ascending, batch index descending; load_data.py:117-125). */
@@ -174,6 +177,18 @@ int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
                     const float *w8, const float *b_alpha, const float *g_agg, float *g_hidden,
                     float *node_small, float *g_rela, float *g_ar8, const rg_heavy *heavy,
                     void *stream);
+
+/* ---- node update: models.py:41 (act(W_h agg)), :81 (h0 re-index), :83 (single-step nn.GRU, gate
+ *      order r,z,n; dropout :82 is the identity in eval mode), next layer's Ws_attn(hidden) and
+ *      :86 W_final(hidden).  Inference only (no saved state for autograd).
+ *   hidden[j] = GRU(act(W_h agg[j]), src[j] >= 0 ? h_prev[src[j]] : 0)
+ *   as8[j]    = Ws_next[8][D] . hidden[j]     (optional; rows >= attn_dim of Ws_next are zero)
+ *   score[j]  = W_final[D] . hidden[j]        (optional)
+ * h_prev and src are both NULL at layer 0 (h0 == 0).  act: 0 identity, 1 relu, 2 tanh. */
+int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const float *agg, const float *h_prev,
+                   const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
+                   const float *b_ih, const float *b_hh, const float *Ws_next, const float *W_final,
+                   int32_t act, float *hidden, float *as8, float *score, void *stream);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,8 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "rg_frontier_nodes": (C.c_int, [C.POINTER(RgFrontier), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rg_frontier_remap": (C.c_int, [C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p, C.c_void_p,
-                                    C.c_void_p]),
+                                    C.c_void_p, C.c_void_p]),
+    "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 10 + [C.c_int32] + [C.c_void_p] * 4),
     "rg_edges_emit": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p,
                                 C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p]),
     "rg_edge_agg_fwd": (C.c_int, [C.POINTER(RgSegments), C.c_int32] + [C.c_void_p] * 8

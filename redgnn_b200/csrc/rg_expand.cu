@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kBlock) k_emit_nodes(const uint32_t *__restric
 
 __global__ void __launch_bounds__(kBlock) k_remap(const uint32_t *__restrict__ din,
                                                   const uint32_t *__restrict__ dout, int64_t n_words,
-                                                  int64_t *remap64, int32_t *remap32) {
+                                                  int64_t *remap64, int32_t *remap32, int32_t *inverse32) {
     int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i >= n_words) return;
     uint2 a = reinterpret_cast<const uint2 *>(din)[i];
@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kBlock) k_remap(const uint32_t *__restrict__ d
         uint32_t r = o.y + __popc(o.x & ((1u << bit) - 1u));
         if (remap64) remap64[pos] = (int64_t)r;
         if (remap32) remap32[pos] = (int32_t)r;
+        if (inverse32) inverse32[r] = (int32_t)pos;
         ++pos;
     }
 }
@@ -358,7 +359,7 @@ int rg_frontier_nodes(const rg_frontier *fr, int64_t *nodes64, int32_t *node_b, 
 }
 
 int rg_frontier_remap(const rg_frontier *in, const rg_frontier *out, int64_t *remap64, int32_t *remap32,
-                      void *stream) {
+                      int32_t *inverse32, void *stream) {
     int rc = check_frontier(in);
     if (rc) return rc;
     rc = check_frontier(out);
@@ -366,7 +367,8 @@ int rg_frontier_remap(const rg_frontier *in, const rg_frontier *out, int64_t *re
     if (in->n_query != out->n_query || in->n_ent != out->n_ent) return RG_ERR_BAD_ARG;
     const int64_t n_words = (int64_t)in->n_query * rg_words_ent(in->n_ent);
     k_remap<<<(unsigned)rg_cdiv(n_words, kBlock), kBlock, 0, (cudaStream_t)stream>>>(in->dict, out->dict,
-                                                                                    n_words, remap64, remap32);
+                                                                                    n_words, remap64, remap32,
+                                                                                    inverse32);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }

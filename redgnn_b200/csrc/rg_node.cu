@@ -1,0 +1,265 @@
+// Fused node update: everything RED_GNN_*.forward does per NODE after the edge aggregation
+// (reference Static/transductive/models.py:41 and :81-86):
+//     x      = act(W_h . agg[j])                       GNNLayer.forward :41
+//     h0[j]  = hidden_prev[src[j]]  (0 for new nodes)  zeros().index_copy_(1, old_nodes_new_idx, h0) :81
+//     hidden = GRU_cell(x, h0[j])                      self.gate :83   (dropout :82 is identity in eval)
+//     as8    = Ws_next . hidden                        the next layer's Ws_attn(hs), hoisted per node
+//     score  = W_final . hidden                        :86 (last layer)
+// One persistent CTA keeps all weights in shared memory (transposed, conflict-free) and walks tiles
+// of 64 nodes; each thread owns an 8-row x (D/16)-column register tile, so the three small GEMMs run
+// at FMA rate out of shared memory and the D-float rows touch HBM exactly once (read agg, read
+// h_prev row, write hidden).  Inference only: training keeps the torch-composed path so autograd
+// sees it.
+#include <algorithm>
+
+#include "rg_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;  // 16 column groups x 8 row groups
+constexpr int kTM = 64;        // nodes per tile
+constexpr int kRT = 8;         // rows per thread
+
+template <int D>
+struct NodeSmem {
+    static constexpr int S = D + 1;  // padded row stride of the activation tiles
+    // float offsets
+    static constexpr int WhT = 0;                  // [D][D]
+    static constexpr int WihT = WhT + D * D;       // [D][3D]
+    static constexpr int WhhT = WihT + D * 3 * D;  // [D][3D]
+    static constexpr int Brz = WhhT + D * 3 * D;   // [2D] b_ih + b_hh of the r and z gates
+    static constexpr int Bin = Brz + 2 * D;        // [D]
+    static constexpr int Bhn = Bin + D;            // [D]
+    static constexpr int Ws = Bhn + D;             // [9][D] rows 0..7 = Ws_next, row 8 = W_final
+    static constexpr int A = Ws + 9 * D;           // [TM][S] agg tile, later the hidden tile
+    static constexpr int X = A + kTM * S;          // [TM][S]
+    static constexpr int H0 = X + kTM * S;         // [TM][S]
+    static constexpr int Total = H0 + kTM * S;
+};
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return tanhf(v);
+    return v;
+}
+
+__device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+template <int D, bool HAS_H0>
+__global__ void __launch_bounds__(kThreads) k_node_update(
+    const float *__restrict__ agg, const float *__restrict__ h_prev, const int32_t *__restrict__ src,
+    const float *__restrict__ W_h, const float *__restrict__ W_ih, const float *__restrict__ W_hh,
+    const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ Ws_next,
+    const float *__restrict__ W_final, int act, int64_t n_nodes, float *__restrict__ hidden,
+    float *__restrict__ as8, float *__restrict__ score) {
+    extern __shared__ float sm[];
+    using L = NodeSmem<D>;
+    constexpr int S = L::S, CT = D / 16;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+    // ---- weights -> shared memory, transposed to [k][col] ----
+    for (int i = tid; i < D * D; i += kThreads) {
+        int c = i / D, k = i % D;
+        sm[L::WhT + k * D + c] = W_h[i];
+    }
+    for (int i = tid; i < 3 * D * D; i += kThreads) {
+        int c = i / D, k = i % D;  // c in [0, 3D): gate-major output column
+        sm[L::WihT + k * 3 * D + c] = W_ih[i];
+        sm[L::WhhT + k * 3 * D + c] = HAS_H0 ? W_hh[i] : 0.f;
+    }
+    for (int i = tid; i < 2 * D; i += kThreads) sm[L::Brz + i] = b_ih[i] + b_hh[i];
+    for (int i = tid; i < D; i += kThreads) {
+        sm[L::Bin + i] = b_ih[2 * D + i];
+        sm[L::Bhn + i] = b_hh[2 * D + i];
+    }
+    for (int i = tid; i < 9 * D; i += kThreads) {
+        float v = 0.f;
+        if (i < 8 * D) {
+            if (Ws_next) v = Ws_next[i];
+        } else if (W_final) {
+            v = W_final[i - 8 * D];
+        }
+        sm[L::Ws + i] = v;
+    }
+    __syncthreads();
+
+    const int64_t n_tiles = (n_nodes + kTM - 1) / kTM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * kTM;
+        const int rows = (int)min((int64_t)kTM, n_nodes - row0);
+        // ---- stage agg rows and the re-indexed previous state ----
+        constexpr int V = D / 4;  // float4 per row
+        for (int i = tid; i < kTM * V; i += kThreads) {
+            const int r = i / V, v = i % V;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), h = a;
+            if (r < rows) {
+                a = __ldg(reinterpret_cast<const float4 *>(agg + (size_t)(row0 + r) * D) + v);
+                if (HAS_H0) {
+                    const int s = __ldg(src + row0 + r);
+                    if (s >= 0) h = __ldg(reinterpret_cast<const float4 *>(h_prev + (size_t)s * D) + v);
+                }
+            }
+            float *pa = sm + L::A + r * S + v * 4;
+            pa[0] = a.x; pa[1] = a.y; pa[2] = a.z; pa[3] = a.w;
+            float *ph = sm + L::H0 + r * S + v * 4;
+            ph[0] = h.x; ph[1] = h.y; ph[2] = h.z; ph[3] = h.w;
+        }
+        __syncthreads();
+
+        // ---- phase A: X = act(agg . W_h^T) ----
+        {
+            float acc[kRT][CT];
+#pragma unroll
+            for (int i = 0; i < kRT; ++i)
+#pragma unroll
+                for (int j = 0; j < CT; ++j) acc[i][j] = 0.f;
+            const float *pa = sm + L::A + (ty * kRT) * S;
+#pragma unroll 4
+            for (int k = 0; k < D; ++k) {
+                float w[CT];
+#pragma unroll
+                for (int j = 0; j < CT; ++j) w[j] = sm[L::WhT + k * D + tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) {
+                    const float a = pa[i * S + k];
+#pragma unroll
+                    for (int j = 0; j < CT; ++j) acc[i][j] = fmaf(a, w[j], acc[i][j]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kRT; ++i)
+#pragma unroll
+                for (int j = 0; j < CT; ++j)
+                    sm[L::X + (ty * kRT + i) * S + tx + 16 * j] = act_apply(acc[i][j], act);
+        }
+        __syncthreads();
+
+        // ---- phase B: GRU cell ----
+        {
+            float aR[kRT][CT], aZ[kRT][CT], aI[kRT][CT], aH[kRT][CT];
+#pragma unroll
+            for (int i = 0; i < kRT; ++i)
+#pragma unroll
+                for (int j = 0; j < CT; ++j) aR[i][j] = aZ[i][j] = aI[i][j] = aH[i][j] = 0.f;
+            const float *px = sm + L::X + (ty * kRT) * S;
+            const float *ph = sm + L::H0 + (ty * kRT) * S;
+#pragma unroll 2
+            for (int k = 0; k < D; ++k) {
+                float wir[CT], wiz[CT], win[CT], whr[CT], whz[CT], whn[CT];
+                const float *wi = sm + L::WihT + k * 3 * D + tx;
+                const float *wh = sm + L::WhhT + k * 3 * D + tx;
+#pragma unroll
+                for (int j = 0; j < CT; ++j) {
+                    wir[j] = wi[16 * j];
+                    wiz[j] = wi[D + 16 * j];
+                    win[j] = wi[2 * D + 16 * j];
+                    if (HAS_H0) {
+                        whr[j] = wh[16 * j];
+                        whz[j] = wh[D + 16 * j];
+                        whn[j] = wh[2 * D + 16 * j];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kRT; ++i) {
+                    const float x = px[i * S + k];
+                    const float h = HAS_H0 ? ph[i * S + k] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < CT; ++j) {
+                        aR[i][j] = fmaf(x, wir[j], aR[i][j]);
+                        aZ[i][j] = fmaf(x, wiz[j], aZ[i][j]);
+                        aI[i][j] = fmaf(x, win[j], aI[i][j]);
+                        if (HAS_H0) {
+                            aR[i][j] = fmaf(h, whr[j], aR[i][j]);
+                            aZ[i][j] = fmaf(h, whz[j], aZ[i][j]);
+                            aH[i][j] = fmaf(h, whn[j], aH[i][j]);
+                        }
+                    }
+                }
+            }
+            // gates; the hidden tile overwrites the agg tile (free since the barrier after phase A)
+#pragma unroll
+            for (int i = 0; i < kRT; ++i) {
+                const int r = ty * kRT + i;
+#pragma unroll
+                for (int j = 0; j < CT; ++j) {
+                    const int c = tx + 16 * j;
+                    const float rg = sigmoid_precise(aR[i][j] + sm[L::Brz + c]);
+                    const float zg = sigmoid_precise(aZ[i][j] + sm[L::Brz + D + c]);
+                    const float ng = tanhf(aI[i][j] + sm[L::Bin + c] + rg * (aH[i][j] + sm[L::Bhn + c]));
+                    const float h0 = HAS_H0 ? sm[L::H0 + r * S + c] : 0.f;
+                    const float hn = (1.0f - zg) * ng + zg * h0;
+                    sm[L::A + r * S + c] = hn;
+                    if (r < rows) hidden[(size_t)(row0 + r) * D + c] = hn;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase C: next layer's attention projection and / or the final score ----
+        if (as8 || score) {
+            for (int o = tid; o < kTM * 9; o += kThreads) {
+                const int r = o / 9, a = o % 9;
+                if (r >= rows) continue;
+                if (a < 8 ? (as8 == nullptr) : (score == nullptr)) continue;
+                const float *ph = sm + L::A + r * S;
+                const float *pw = sm + L::Ws + a * D;
+                float s = 0.f;
+#pragma unroll 8
+                for (int k = 0; k < D; ++k) s = fmaf(ph[k], pw[k], s);
+                if (a < 8)
+                    as8[(size_t)(row0 + r) * 8 + a] = s;
+                else
+                    score[row0 + r] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int D, bool HH>
+int launch_node(const float *agg, const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
+                const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
+                const float *W_final, int act, int64_t n_nodes, float *hidden, float *as8, float *score,
+                cudaStream_t st) {
+    constexpr size_t smem = sizeof(float) * NodeSmem<D>::Total;
+    auto kern = k_node_update<D, HH>;
+    RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, n_sm = 148, per_sm = 1;
+    RG_CUDA_CALL(cudaGetDevice(&dev));
+    RG_CUDA_CALL(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    RG_CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_tiles = (n_nodes + kTM - 1) / kTM;
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)n_sm * per_sm);
+    kern<<<grid, kThreads, smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
+                                       n_nodes, hidden, as8, score);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
+
+}  // namespace
+
+extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const float *agg, const float *h_prev,
+                              const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
+                              const float *b_ih, const float *b_hh, const float *Ws_next, const float *W_final,
+                              int32_t act, float *hidden, float *as8, float *score, void *stream) {
+    if (n_nodes < 0 || !agg || !W_h || !W_ih || !W_hh || !b_ih || !b_hh || !hidden) return RG_ERR_BAD_ARG;
+    if ((h_prev == nullptr) != (src == nullptr)) return RG_ERR_BAD_ARG;
+    if ((as8 != nullptr) != (Ws_next != nullptr) || (score != nullptr) != (W_final != nullptr)) return RG_ERR_BAD_ARG;
+    if (act < 0 || act > 2) return RG_ERR_BAD_ARG;
+    if (n_nodes == 0) return RG_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define RG_NODE(DD)                                                                                              \
+    return h_prev ? launch_node<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,   \
+                                          n_nodes, hidden, as8, score, st)                                       \
+                  : launch_node<DD, false>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,  \
+                                           n_nodes, hidden, as8, score, st)
+    switch (hidden_dim) {
+        case 16: RG_NODE(16);
+        case 32: RG_NODE(32);
+        case 48: RG_NODE(48);
+        case 64: RG_NODE(64);
+        default: return RG_ERR_UNSUPPORTED;
+    }
+#undef RG_NODE
+}

@@ -169,7 +169,15 @@ class Frontier(object):
 
     def remap_to(self, fr_out, n_nodes):
         out = torch.empty(n_nodes, dtype=torch.int64, device=self.emask.device)
-        check(lib.rg_frontier_remap(C.byref(self.c_struct()), C.byref(fr_out.c_struct()), ptr(out), None,
+        check(lib.rg_frontier_remap(C.byref(self.c_struct()), C.byref(fr_out.c_struct()), ptr(out), None, None,
                                     stream_ptr()))
         _lib.Stats.launches += 1
         return out
+
+    def inverse_remap_to(self, fr_out, n_out):
+        """int32 [n_out]: row of each `fr_out` node inside this (previous) frontier, -1 for new nodes."""
+        inv = torch.full((n_out,), -1, dtype=torch.int32, device=self.emask.device)
+        check(lib.rg_frontier_remap(C.byref(self.c_struct()), C.byref(fr_out.c_struct()), None, None, ptr(inv),
+                                    stream_ptr()))
+        _lib.Stats.launches += 1
+        return inv

@@ -11,7 +11,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .ops import Segments, edge_aggregate
+from .ops import Segments, edge_aggregate, edge_agg_forward, node_update, ACT_CODES
 
 SUPPORTED_DIMS = (16, 32, 48, 64)
 
@@ -82,6 +82,7 @@ class RedGNN(torch.nn.Module):
         self.loader = loader
         acts = {'relu': nn.ReLU(), 'tanh': torch.tanh, 'idd': lambda x: x}
         act = acts[params.act]
+        self.act_name = params.act
 
         self.gnn_layers = nn.ModuleList([GNNLayer(self.hidden_dim, self.hidden_dim, self.attn_dim, self.n_rel, act=act)
                                          for _ in range(self.n_layer)])
@@ -123,8 +124,11 @@ class RedGNN(torch.nn.Module):
         fr = graph.frontier_from_nodes(torch.stack([batch, q_sub], dim=1), n)
         node_b, node_e = batch.to(torch.int32), q_sub.to(torch.int32)
         n_nodes = n
-        h0 = torch.zeros((n, d), device=dev)
-        hidden = None
+        # inference: per-node work (W_h, act, h0 re-index, GRU, next Ws_attn, W_final) runs in the fused
+        # node kernel; with autograd on (or active dropout) it stays torch-composed so autograd sees it
+        fused = not need_grad and not (self.training and self.dropout.p > 0)
+        h0 = None if fused else torch.zeros((n, d), device=dev)
+        hidden, as8, scores = None, None, None
         edges_per_layer = []
         for i in range(self.n_layer):
             fr_next = graph.step(fr)
@@ -132,22 +136,39 @@ class RedGNN(torch.nn.Module):
             if err:
                 raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % graph.n_ent)
             nb, ne = fr_next.nodes32(n_next)
-            remap = fr.remap_to(fr_next, n_nodes)
             fwd_seg = Segments.implicit(nb, ne, graph.in_ptr, graph.in_adj, fr, graph.heavy_in)
-            bwd_seg = Segments.implicit(node_b, node_e, graph.out_ptr, graph.out_adj, fr_next, graph.heavy_out) \
-                if need_grad else None
             fwd_seg.n_edges = n_edges
-            if bwd_seg is not None:
-                bwd_seg.n_edges = n_edges
-            hidden = self.gnn_layers[i].propagate(q_rel, hidden, fwd_seg, bwd_seg)
-            h0 = torch.zeros((n_next, d), device=dev).index_copy_(0, remap, h0)
-            hidden = self.dropout(hidden)
-            hidden = self._gate(hidden, h0)
-            h0 = hidden
+            layer = self.gnn_layers[i]
+            if fused:
+                rela = layer.rela_embed.weight
+                ar8 = _pad8(layer.Wr_attn(rela))
+                aq8 = _pad8(layer.Wqr_attn(rela[q_rel]))
+                w8 = _pad8(layer.w_alpha.weight).reshape(8)
+                agg = edge_agg_forward(fwd_seg, hidden, as8, rela.contiguous(), ar8.contiguous(), aq8.contiguous(),
+                                       w8.contiguous(), layer.w_alpha.bias)
+                last = i == self.n_layer - 1
+                ws_next = None if last else F.pad(self.gnn_layers[i + 1].Ws_attn.weight,
+                                                  (0, 0, 0, 8 - self.attn_dim)).contiguous()
+                src = fr.inverse_remap_to(fr_next, n_next) if hidden is not None else None
+                hidden, as8, scores = node_update(agg, hidden, src, layer.W_h.weight, self.gate,
+                                                  ACT_CODES[self.act_name], ws_next,
+                                                  self.W_final.weight if last else None)
+            else:
+                remap = fr.remap_to(fr_next, n_nodes)
+                bwd_seg = None
+                if need_grad:
+                    bwd_seg = Segments.implicit(node_b, node_e, graph.out_ptr, graph.out_adj, fr_next, graph.heavy_out)
+                    bwd_seg.n_edges = n_edges
+                hidden = layer.propagate(q_rel, hidden, fwd_seg, bwd_seg)
+                h0 = torch.zeros((n_next, d), device=dev).index_copy_(0, remap, h0)
+                hidden = self.dropout(hidden)
+                hidden = self._gate(hidden, h0)
+                h0 = hidden
             fr, node_b, node_e, n_nodes = fr_next, nb, ne, n_next
             edges_per_layer.append(n_edges)
 
-        scores = self.W_final(hidden).squeeze(-1)
+        if not fused:
+            scores = self.W_final(hidden).squeeze(-1)
         scores_all = torch.zeros((n, n_ent_out), device=dev)
         scores_all[node_b.long(), node_e.long()] = scores
         self.last_stats = {"edges": edges_per_layer, "nodes": n_nodes}

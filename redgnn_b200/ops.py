@@ -121,6 +121,26 @@ def edge_agg_backward(bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, 
     return g_hidden, (g_as8.contiguous() if hidden is not None else None), g_rela, g_ar8, g_aq8, g_w8, g_b
 
 
+ACT_CODES = {"idd": 0, "relu": 1, "tanh": 2}
+
+
+def node_update(agg, h_prev, src, W_h, gate, act_code, Ws_next8=None, W_final=None):
+    """Fused inference node update (rg_node_update): returns (hidden, as8 | None, score | None).
+    gate: the nn.GRU module (weight_ih_l0 [3D,D], weight_hh_l0, bias_ih_l0, bias_hh_l0)."""
+    _lib.require_cuda(agg, h_prev, src, W_h)
+    n, d = agg.shape
+    hidden = torch.empty((n, d), dtype=torch.float32, device=agg.device)
+    as8 = torch.empty((n, 8), dtype=torch.float32, device=agg.device) if Ws_next8 is not None else None
+    score = torch.empty((n,), dtype=torch.float32, device=agg.device) if W_final is not None else None
+    with _lib.Stats.timed("node_update", (n, d)):
+        check(lib.rg_node_update(d, n, ptr(agg), ptr(h_prev), ptr(src), ptr(_f32c(W_h)), ptr(_f32c(gate.weight_ih_l0)),
+                                 ptr(_f32c(gate.weight_hh_l0)), ptr(_f32c(gate.bias_ih_l0)),
+                                 ptr(_f32c(gate.bias_hh_l0)), ptr(Ws_next8), ptr(_f32c(W_final)), act_code,
+                                 ptr(hidden), ptr(as8), ptr(score), stream_ptr()))
+    _lib.Stats.launches += 1
+    return hidden, as8, score
+
+
 class EdgeAggregate(torch.autograd.Function):
     """agg[s] = sum_{edges e into s} alpha_e * (hidden[p_e] + rela[r_e]),
     alpha_e = sigmoid(b_alpha + sum_k w8[k] relu(as8[p_e][k] + ar8[r_e][k] + aq8[q_e][k]))."""

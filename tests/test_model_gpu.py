@@ -176,3 +176,54 @@ def test_golden_fb237_v2_scores(tmp_path):
     torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1))).backward()
     for k, p in model.named_parameters():
         assert_close(p.grad, torch.from_numpy(fx["train_grad." + k]), 1e-4, "fb237_v2 grad " + k)
+
+
+@pytest.mark.parametrize("act,d,a,n_layer", [("relu", 48, 5, 3), ("tanh", 32, 3, 4), ("idd", 64, 5, 2),
+                                             ("relu", 16, 8, 3)])
+def test_fused_inference_path_vs_oracle(tiny_dir, act, d, a, n_layer):
+    """torch.no_grad(): the per-node work runs in the fused rg_node_update kernel."""
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans, _lib
+    L, D = TransductiveLoader(tiny_dir), O.TransductiveData(tiny_dir)
+    sd = O.init_state_dict(n_layer, d, a, D.n_rel, seed=11)
+    model = RED_GNN_trans(Options(hidden_dim=d, attn_dim=a, n_layer=n_layer, dropout=0.2, act=act, n_rel=L.n_rel),
+                          L).cuda()
+    model.load_state_dict(sd)
+    model.eval()
+    subs, rels, _ = L.get_batch(np.arange(70), data="test")
+    _lib.Stats.timing = []
+    with torch.no_grad():
+        got = model(subs, rels, mode="test")
+    names = [t[0] for t in _lib.Stats.timing]
+    _lib.Stats.timing = None
+    assert names.count("node_update") == n_layer and names.count("edge_fwd") == n_layer
+    want = O.model_forward(sd, D.test_graph, subs, rels, n_layer, act)
+    assert_close(got, want, 1e-4, "fused scores")
+    assert torch.equal(got.cpu() == 0, want == 0)
+    assert_close(got, model(subs, rels, mode="test"), 1e-5, "fused vs torch-composed path")
+    with torch.no_grad():
+        assert torch.equal(got, model(subs, rels, mode="test")), "inference must be bit-reproducible"
+
+
+def test_fused_inference_golden_family_and_hub(tmp_path, hub_dir):
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    fx = golden("family")
+    L = TransductiveLoader(write_family_dir(tmp_path, fx))
+    model = RED_GNN_trans(Options(n_rel=L.n_rel, dropout=0.29), L).cuda()
+    model.load_state_dict(golden_state_dict(fx))
+    model.eval()
+    with torch.no_grad():
+        scores = model(fx["eval_subs"], fx["eval_rels"], mode="test")
+    want = torch.from_numpy(fx["eval_scores"])
+    assert_close(scores, want, 1e-4, "family fused scores")
+    assert torch.equal(scores.cpu() == 0, want == 0)
+    ranks = O.cal_ranks(scores.cpu().numpy(), fx["eval_objs"].astype(np.float64), fx["eval_filters"].astype(np.float64))
+    assert np.array_equal(np.array(ranks), fx["eval_ranks"])
+    L2, D2 = TransductiveLoader(hub_dir), O.TransductiveData(hub_dir)
+    sd = O.init_state_dict(3, 48, 5, D2.n_rel, seed=9)
+    m2 = RED_GNN_trans(Options(n_rel=L2.n_rel), L2).cuda()
+    m2.load_state_dict(sd)
+    m2.eval()
+    subs, rels, _ = L2.get_batch(np.arange(8), data="valid")
+    with torch.no_grad():
+        got = m2(subs, rels, mode="valid")
+    assert_close(got, O.model_forward(sd, D2.test_graph, subs, rels, 3, "relu"), 1e-4, "hub fused scores")
