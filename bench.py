@@ -136,7 +136,7 @@ def run_reference(args):
     qps = nq * args.steps / dt
     sample = "%d queries/step x %d steps of the %s workload, oracle port of the reference CPU path" % (
         nq, args.steps, args.workload)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -145,7 +145,7 @@ def run_reference(args):
                    "hidden_dim": HIDDEN, "attn_dim": ATTN, "n_layer": n_layer},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def workload_name(workload, n_layer):
@@ -155,8 +155,30 @@ def workload_name(workload, n_layer):
         workload, ne, nr, nt, n_layer)
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """Libraries (NCCL, torch.distributed) print banners to stdout; the contract is ONE JSON line there.
+    Route fd 1 to stderr for the whole run and keep a private handle for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse_args()
+    guard_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -259,7 +281,9 @@ def main():
     for name, meta, a, b in timing:
         if name != "edge_fwd":
             continue
-        n_seg, d, has_hidden, e_l = meta
+        seg, d, has_hidden = meta
+        fr = getattr(seg, "frontier", None)          # sync-free path: counts resolved by model.last_stats
+        n_seg, e_l = (fr.n_nodes, fr.n_edges) if fr is not None else (seg.n_seg, seg.n_edges)
         edge_ms += a.elapsed_time(b)
         edge_bytes += ((16 + 4 * d) if has_hidden else 16) * e_l + 4 * d * n_seg
 
@@ -342,7 +366,7 @@ def main():
                                 "edges_per_s": edges_cpu / dt,
                                 "sample": "%d batches of %d queries of the same workload through the oracle port "
                                           "(scipy SpGEMM + torch.unique + torch CPU), %.1f s" % (reps, nq, dt)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -89,7 +89,8 @@ typedef struct rg_frontier {
 typedef struct rg_segments {
     int32_t mode;
     int32_t n_ent;                 /* implicit: dictionary row length We = ceil(n_ent/32)      */
-    int64_t n_seg;
+    int64_t n_seg;                 /* number of segments (an UPPER BOUND when n_seg_dev is set) */
+    const int64_t *n_seg_dev;      /* optional device-resident true count (no host read-back)  */
     const int32_t *seg_query;      /* [n_seg]                                                  */
     const int32_t *seg_ptr;        /* explicit: [n_seg+1]                                      */
     const int32_t *adj;            /* explicit: [E][2]; implicit: ent_adj [F][2]               */
@@ -184,11 +185,19 @@ int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
  *   hidden[j] = GRU(act(W_h agg[j]), src[j] >= 0 ? h_prev[src[j]] : 0)
  *   as8[j]    = Ws_next[8][D] . hidden[j]     (optional; rows >= attn_dim of Ws_next are zero)
  *   score[j]  = W_final[D] . hidden[j]        (optional)
- * h_prev and src are both NULL at layer 0 (h0 == 0).  act: 0 identity, 1 relu, 2 tanh. */
-int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const float *agg, const float *h_prev,
+ * h_prev and src are both NULL at layer 0 (h0 == 0).  act: 0 identity, 1 relu, 2 tanh.
+ * n_nodes is an upper bound when n_nodes_dev (device-resident true count) is given. */
+int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
+                   const float *h_prev,
                    const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                    const float *b_ih, const float *b_hh, const float *Ws_next, const float *W_final,
                    int32_t act, float *hidden, float *as8, float *score, void *stream);
+
+/* scores_all[node_b[j]][node_e[j]] = score[j] for j < n (models.py:87-88; scores_all is zeroed by
+ * the caller, so unvisited entities keep an exact 0). */
+int rg_scatter_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
+                      const int32_t *node_e, const float *score, int32_t n_ent_out, float *scores_all,
+                      void *stream);
 
 #ifdef __cplusplus
 }

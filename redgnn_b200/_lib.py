@@ -28,7 +28,7 @@ class RgFrontier(C.Structure):
 
 
 class RgSegments(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("n_ent", C.c_int32), ("n_seg", C.c_int64),
+    _fields_ = [("mode", C.c_int32), ("n_ent", C.c_int32), ("n_seg", C.c_int64), ("n_seg_dev", C.c_void_p),
                 ("seg_query", C.c_void_p), ("seg_ptr", C.c_void_p), ("adj", C.c_void_p),
                 ("seg_ent", C.c_void_p), ("ent_ptr", C.c_void_p), ("peer_dict", C.c_void_p)]
 
@@ -53,7 +53,8 @@ SIGNATURES = {
     "rg_frontier_nodes": (C.c_int, [C.POINTER(RgFrontier), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rg_frontier_remap": (C.c_int, [C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
-    "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 10 + [C.c_int32] + [C.c_void_p] * 4),
+    "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 4),
+    "rg_scatter_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
     "rg_edges_emit": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p,
                                 C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p]),
     "rg_edge_agg_fwd": (C.c_int, [C.POINTER(RgSegments), C.c_int32] + [C.c_void_p] * 8

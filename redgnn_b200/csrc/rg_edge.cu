@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kBlock) k_edge_fwd(rg_segments S, const float 
                                                      float *__restrict__ agg, rg_heavy H, int has_heavy) {
     const int lane = threadIdx.x & 31;
     const int64_t seg = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (seg >= S.n_seg) return;
+    if (seg >= (S.n_seg_dev ? *S.n_seg_dev : S.n_seg)) return;
     SegRange r = seg_range<IMPLICIT>(S, seg);
     int hi = r.hi;
     if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
                                                      int has_heavy) {
     const int lane = threadIdx.x & 31;
     const int64_t seg = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (seg >= S.n_seg) return;
+    if (seg >= (S.n_seg_dev ? *S.n_seg_dev : S.n_seg)) return;
     SegRange r = seg_range<IMPLICIT>(S, seg);
     int hi = r.hi;
     if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all

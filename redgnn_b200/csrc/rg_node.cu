@@ -50,9 +50,10 @@ __global__ void __launch_bounds__(kThreads) k_node_update(
     const float *__restrict__ agg, const float *__restrict__ h_prev, const int32_t *__restrict__ src,
     const float *__restrict__ W_h, const float *__restrict__ W_ih, const float *__restrict__ W_hh,
     const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ Ws_next,
-    const float *__restrict__ W_final, int act, int64_t n_nodes, float *__restrict__ hidden,
-    float *__restrict__ as8, float *__restrict__ score) {
+    const float *__restrict__ W_final, int act, int64_t n_nodes_host, const int64_t *__restrict__ n_nodes_dev,
+    float *__restrict__ hidden, float *__restrict__ as8, float *__restrict__ score) {
     extern __shared__ float sm[];
+    const int64_t n_nodes = n_nodes_dev ? *n_nodes_dev : n_nodes_host;
     using L = NodeSmem<D>;
     constexpr int S = L::S, CT = D / 16;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(kThreads) k_node_update(
 template <int D, bool HH>
 int launch_node(const float *agg, const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                 const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
-                const float *W_final, int act, int64_t n_nodes, float *hidden, float *as8, float *score,
-                cudaStream_t st) {
+                const float *W_final, int act, int64_t n_nodes, const int64_t *n_nodes_dev, float *hidden,
+                float *as8, float *score, cudaStream_t st) {
     constexpr size_t smem = sizeof(float) * NodeSmem<D>::Total;
     auto kern = k_node_update<D, HH>;
     RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -232,14 +233,36 @@ int launch_node(const float *agg, const float *h_prev, const int32_t *src, const
     const int64_t n_tiles = (n_nodes + kTM - 1) / kTM;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)n_sm * per_sm);
     kern<<<grid, kThreads, smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
-                                       n_nodes, hidden, as8, score);
+                                       n_nodes, n_nodes_dev, hidden, as8, score);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
 
 }  // namespace
 
-extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const float *agg, const float *h_prev,
+__global__ void __launch_bounds__(256) k_scatter_scores(int64_t n_host, const int64_t *__restrict__ n_dev,
+                                                        const int32_t *__restrict__ node_b,
+                                                        const int32_t *__restrict__ node_e,
+                                                        const float *__restrict__ score, int n_ent_out,
+                                                        float *__restrict__ out) {
+    const int64_t n = n_dev ? *n_dev : n_host;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[(size_t)node_b[i] * n_ent_out + node_e[i]] = score[i];
+}
+
+extern "C" int rg_scatter_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
+                                 const int32_t *node_e, const float *score, int32_t n_ent_out,
+                                 float *scores_all, void *stream) {
+    if (n_nodes < 0 || !node_b || !node_e || !score || !scores_all || n_ent_out <= 0) return RG_ERR_BAD_ARG;
+    if (n_nodes == 0) return RG_OK;
+    k_scatter_scores<<<(unsigned)rg_cdiv(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(
+        n_nodes, n_nodes_dev, node_b, node_e, score, n_ent_out, scores_all);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
+
+extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
+                              const float *h_prev,
                               const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                               const float *b_ih, const float *b_hh, const float *Ws_next, const float *W_final,
                               int32_t act, float *hidden, float *as8, float *score, void *stream) {
@@ -251,9 +274,9 @@ extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const float *
     cudaStream_t st = (cudaStream_t)stream;
 #define RG_NODE(DD)                                                                                              \
     return h_prev ? launch_node<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,   \
-                                          n_nodes, hidden, as8, score, st)                                       \
+                                          n_nodes, n_nodes_dev, hidden, as8, score, st)                                       \
                   : launch_node<DD, false>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,  \
-                                           n_nodes, hidden, as8, score, st)
+                                           n_nodes, n_nodes_dev, hidden, as8, score, st)
     switch (hidden_dim) {
         case 16: RG_NODE(16);
         case 32: RG_NODE(32);

@@ -133,7 +133,8 @@ class Frontier(object):
         self.emask = torch.empty(lib.rg_frontier_emask_bytes(n_query, n_ent) // 4, dtype=torch.int32, device=device)
         self.dict = torch.empty(lib.rg_frontier_dict_bytes(n_query, n_ent) // 4, dtype=torch.int32, device=device)
         self.counts = torch.zeros(_lib.RG_COUNTS_WORDS, dtype=torch.int64, device=device)
-        self.n_nodes = None
+        self.n_nodes = None      # host copies of the hop counts, filled by read_counts() / RedGNN.last_stats
+        self.n_edges = None
         self._c = None
 
     def c_struct(self):

@@ -22,6 +22,7 @@ class Segments(object):
         self.seg_ptr, self.seg_ent, self.ent_ptr, self.peer_dict = seg_ptr, seg_ent, ent_ptr, peer_dict
         self.heavy_bound = (int(heavy_bound[0]), int(heavy_bound[1]))   # (max_chunks, max_nodes)
         self.n_edges = int(adj.shape[0]) if mode == 0 else None       # implicit: set by the caller if known
+        self.n_seg_dev = None      # optional int64 device scalar: true segment count (n_seg = upper bound)
         self._c = None
 
     @staticmethod
@@ -53,7 +54,9 @@ class Segments(object):
 
     def c_struct(self):
         if self._c is None:
-            self._c = _lib.RgSegments(self.mode, self.n_ent, self.n_seg, self.seg_query.data_ptr(),
+            self._c = _lib.RgSegments(self.mode, self.n_ent, self.n_seg,
+                                      self.n_seg_dev.data_ptr() if self.n_seg_dev is not None else None,
+                                      self.seg_query.data_ptr(),
                                       self.seg_ptr.data_ptr() if self.seg_ptr is not None else None,
                                       self.adj.data_ptr(),
                                       self.seg_ent.data_ptr() if self.seg_ent is not None else None,
@@ -91,7 +94,7 @@ def edge_agg_forward(fwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha):
     d = rela.shape[1]
     agg = torch.empty((fwd_seg.n_seg, d), dtype=torch.float32, device=rela.device)
     heavy = _Heavy(fwd_seg.heavy_bound, d, rela.device)
-    with _lib.Stats.timed("edge_fwd", (fwd_seg.n_seg, d, hidden is not None, fwd_seg.n_edges)):
+    with _lib.Stats.timed("edge_fwd", (fwd_seg, d, hidden is not None)):
         check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
                                   ptr(aq8), ptr(w8), ptr(b_alpha), ptr(agg), heavy.ref(), stream_ptr()))
     _lib.Stats.launches += 3 if heavy.struct is not None else 1
@@ -108,7 +111,7 @@ def edge_agg_backward(bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, 
     g_rela = torch.zeros_like(rela)
     g_ar8 = torch.zeros_like(ar8)
     heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
-    with _lib.Stats.timed("edge_bwd", (n_in, d, hidden is not None, bwd_seg.n_edges)):
+    with _lib.Stats.timed("edge_bwd", (bwd_seg, d, hidden is not None)):
         check(lib.rg_edge_agg_bwd(C.byref(bwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
                                   ptr(aq8), ptr(w8), ptr(b_alpha), ptr(g_agg), ptr(g_hidden), ptr(node_small),
                                   ptr(g_rela), ptr(g_ar8), heavy.ref(), stream_ptr()))
@@ -124,7 +127,16 @@ def edge_agg_backward(bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, 
 ACT_CODES = {"idd": 0, "relu": 1, "tanh": 2}
 
 
-def node_update(agg, h_prev, src, W_h, gate, act_code, Ws_next8=None, W_final=None):
+def scatter_scores(node_b, node_e, score, n_query, n_ent_out, n_dev=None):
+    """scores_all (n, n_ent) with exact zeros for unvisited entities (rg_scatter_scores)."""
+    out = torch.zeros((n_query, n_ent_out), dtype=torch.float32, device=score.device)
+    check(lib.rg_scatter_scores(score.shape[0], ptr(n_dev), ptr(node_b), ptr(node_e), ptr(score), n_ent_out,
+                                ptr(out), stream_ptr()))
+    _lib.Stats.launches += 1
+    return out
+
+
+def node_update(agg, h_prev, src, W_h, gate, act_code, Ws_next8=None, W_final=None, n_dev=None):
     """Fused inference node update (rg_node_update): returns (hidden, as8 | None, score | None).
     gate: the nn.GRU module (weight_ih_l0 [3D,D], weight_hh_l0, bias_ih_l0, bias_hh_l0)."""
     _lib.require_cuda(agg, h_prev, src, W_h)
@@ -133,7 +145,7 @@ def node_update(agg, h_prev, src, W_h, gate, act_code, Ws_next8=None, W_final=No
     as8 = torch.empty((n, 8), dtype=torch.float32, device=agg.device) if Ws_next8 is not None else None
     score = torch.empty((n,), dtype=torch.float32, device=agg.device) if W_final is not None else None
     with _lib.Stats.timed("node_update", (n, d)):
-        check(lib.rg_node_update(d, n, ptr(agg), ptr(h_prev), ptr(src), ptr(_f32c(W_h)), ptr(_f32c(gate.weight_ih_l0)),
+        check(lib.rg_node_update(d, n, ptr(n_dev), ptr(agg), ptr(h_prev), ptr(src), ptr(_f32c(W_h)), ptr(_f32c(gate.weight_ih_l0)),
                                  ptr(_f32c(gate.weight_hh_l0)), ptr(_f32c(gate.bias_ih_l0)),
                                  ptr(_f32c(gate.bias_hh_l0)), ptr(Ws_next8), ptr(_f32c(W_final)), act_code,
                                  ptr(hidden), ptr(as8), ptr(score), stream_ptr()))
