@@ -227,3 +227,41 @@ def test_fused_inference_golden_family_and_hub(tmp_path, hub_dir):
     with torch.no_grad():
         got = m2(subs, rels, mode="valid")
     assert_close(got, O.model_forward(sd, D2.test_graph, subs, rels, 3, "relu"), 1e-4, "hub fused scores")
+
+
+def test_cuda_graph_replay_matches_eager_and_tracks_parameters(tiny_dir):
+    """The captured inference forward: new inputs, in-place parameter updates and a new KG
+    (shuffle_train) all give the same scores as the eager sync-free path."""
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans, _lib
+    L = TransductiveLoader(tiny_dir)
+    model = RED_GNN_trans(Options(n_rel=L.n_rel), L).cuda()
+    model.eval()
+    batches = [L.get_batch(np.arange(k * 24, (k + 1) * 24), data="test")[:2] for k in range(3)]
+
+    def eager(subs, rels, mode="test"):
+        model.use_cuda_graph = False
+        try:
+            with torch.no_grad():
+                return model(subs, rels, mode=mode)
+        finally:
+            model.use_cuda_graph = True
+
+    with torch.no_grad():
+        for subs, rels in batches:                       # first call captures, the others replay
+            before = _lib.Stats.launches
+            got = model(subs, rels, mode="test")
+            assert _lib.Stats.launches > before
+            assert torch.equal(got, eager(subs, rels))
+        assert len(model._graph_cache) == 1
+        stats = model.last_stats
+        assert len(stats["edges"]) == 3 and stats["edges"][0] > 0
+        for p in model.parameters():                     # optimiser-style in-place update
+            p.add_(0.01 * torch.randn_like(p))
+        subs, rels = batches[0]
+        assert torch.equal(model(subs, rels, mode="test"), eager(subs, rels))
+        assert len(model._graph_cache) == 1
+        np.random.seed(3)
+        L.shuffle_train()                                # new train graph object -> new capture
+        got = model(subs, rels, mode="train")
+        assert len(model._graph_cache) == 2
+        assert torch.equal(got, eager(subs, rels, "train"))
