@@ -11,6 +11,7 @@
 // h_prev row, write hidden).  Inference only: training keeps the torch-composed path so autograd
 // sees it.
 #include <algorithm>
+#include <cstdlib>
 
 #include "rg_common.cuh"
 
@@ -261,6 +262,12 @@ extern "C" int rg_scatter_scores(int64_t n_nodes, const int64_t *n_nodes_dev, co
     return RG_OK;
 }
 
+// tensor-core (tcgen05 / TMEM, 3xTF32) variant, rg_node_tc.cu
+int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
+                      const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
+                      const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
+                      const float *W_final, int32_t act, float *hidden, float *as8, float *score, cudaStream_t st);
+
 extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
                               const float *h_prev,
                               const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
@@ -272,6 +279,12 @@ extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t
     if (act < 0 || act > 2) return RG_ERR_BAD_ARG;
     if (n_nodes == 0) return RG_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    // default: tensor cores (hidden_dim <= 48 fits one CTA's shared memory); REDGNN_NODE_SIMT=1 forces
+    // the CUDA-core kernel (also the path for hidden_dim 64)
+    const char *force_simt = std::getenv("REDGNN_NODE_SIMT");
+    if (hidden_dim <= 48 && !(force_simt && force_simt[0] == '1'))
+        return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh,
+                                 Ws_next, W_final, act, hidden, as8, score, st);
 #define RG_NODE(DD)                                                                                              \
     return h_prev ? launch_node<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,   \
                                           n_nodes, n_nodes_dev, hidden, as8, score, st)                                       \

@@ -1,0 +1,385 @@
+// Fused node update on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Same contract as k_node_update in rg_node.cu (reference Static/transductive/models.py:41,81-86:
+// x = act(W_h agg), h0 re-index, single-step GRU, next layer's Ws_attn, W_final).  The three dense
+// contractions per node ([1xD].[DxD], [1xD].[Dx3D] twice = 16.5 kFMA at D=48) are the only real
+// GEMMs on the path; on CUDA cores they cost as much as the whole edge kernel.  Here one CTA owns a
+// tile of 128 nodes = the 128 TMEM lanes:
+//   * operands are staged in shared memory in the canonical K-major no-swizzle UMMA layout
+//     (8-row x 16-byte core matrices), each fp32 value split into hi = top 19 bits (what kind::tf32
+//     reads) and lo = x - hi, so that  x.w ~= hi.hi + hi.lo + lo.hi  (3xTF32) keeps fp32-level
+//     accuracy (~2^-19 relative) -- plain TF32 would break the 1e-4 parity bound;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=D/2D/3D, K=8 per
+//     instruction) with fp32 accumulators in TMEM columns [x | r | z | i_n | h_n];
+//   * tcgen05.commit -> mbarrier; all 128 threads (thread t = TMEM lane t = node row t) read their
+//     accumulator row with tcgen05.ld.32x32b, apply the gates, write hidden / as8 / score.
+#include "rg_common.cuh"
+
+namespace {
+
+constexpr int kTcThreads = 128;
+constexpr int kTcRows = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T ; one K=8 TF32 slice
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, no swizzle (INTERLEAVE), sm_100 version bits
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+    return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int D>
+struct TcSmem {
+    static constexpr int KC = D / 4;                 // 16-byte K chunks per row
+    static constexpr int SBO = KC * 128;             // bytes between 8-row groups
+    static constexpr int WROWS = 7 * D;              // W_h (D) | W_ih (3D) | W_hh (3D)
+    static constexpr int W_BYTES = WROWS * D * 4;    // one precision part
+    static constexpr int A_BYTES = kTcRows * D * 4;  // one precision part of one activation tile
+    // byte offsets (all multiples of 128)
+    static constexpr int W_HI = 0;
+    static constexpr int W_LO = W_HI + W_BYTES;
+    static constexpr int A_HI = W_LO + W_BYTES;   // agg, then x
+    static constexpr int A_LO = A_HI + A_BYTES;
+    static constexpr int H_HI = A_LO + A_BYTES;   // h0
+    static constexpr int H_LO = H_HI + A_BYTES;
+    static constexpr int WS = H_LO + A_BYTES;     // float [9][D]
+    static constexpr int BIAS = WS + 9 * D * 4;   // float brz[2D], bin[D], bhn[D]
+    static constexpr int BAR = BIAS + 4 * D * 4;  // uint64 mbarrier, uint32 tmem base
+    static constexpr int TOTAL = BAR + 16;
+    // canonical offset of (row, 16-byte chunk) inside a tile
+    __host__ __device__ static constexpr int off(int row, int chunk) {
+        return ((row >> 3) * KC + chunk) * 128 + (row & 7) * 16;
+    }
+};
+
+__device__ __forceinline__ void split_tf32(float4 x, float4 &hi, float4 &lo) {
+    hi.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+    hi.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+    hi.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+    hi.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+    lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+}
+
+__device__ __forceinline__ float act_apply_tc(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return tanhf(v);
+    return v;
+}
+__device__ __forceinline__ float sigmoid_tc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// issue the 3xTF32 product  D[tmem_d : N cols] (+)= A(rows 0..127) . B(rows b_row0 .. b_row0+N)^T
+template <int D>
+__device__ __forceinline__ void issue_gemm(uint32_t smem_base, int a_hi, int a_lo, int b_row0, int N, uint32_t tmem_d,
+                                           bool accumulate_first) {
+    using L = TcSmem<D>;
+    const uint32_t idesc = make_idesc(kTcRows, N);
+    const uint32_t boff = (uint32_t)(b_row0 >> 3) * L::SBO;
+    uint32_t acc = accumulate_first ? 1u : 0u;
+#pragma unroll
+    for (int ks = 0; ks < D / 8; ++ks) {
+        const uint32_t koff = ks * 256;  // two 16-byte chunks = 8 tf32 values
+        const uint64_t ah = make_desc(smem_base + a_hi + koff, 128, L::SBO);
+        const uint64_t al = make_desc(smem_base + a_lo + koff, 128, L::SBO);
+        const uint64_t bh = make_desc(smem_base + L::W_HI + boff + koff, 128, L::SBO);
+        const uint64_t bl = make_desc(smem_base + L::W_LO + boff + koff, 128, L::SBO);
+        tc_mma_tf32(tmem_d, ah, bh, idesc, acc);
+        tc_mma_tf32(tmem_d, ah, bl, idesc, 1u);
+        tc_mma_tf32(tmem_d, al, bh, idesc, 1u);
+        acc = 1u;
+    }
+}
+
+template <int D, bool HAS_H0>
+__global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
+    const float *__restrict__ agg, const float *__restrict__ h_prev, const int32_t *__restrict__ src,
+    const float *__restrict__ W_h, const float *__restrict__ W_ih, const float *__restrict__ W_hh,
+    const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ Ws_next,
+    const float *__restrict__ W_final, int act, int64_t n_nodes_host, const int64_t *__restrict__ n_nodes_dev,
+    float *__restrict__ hidden, float *__restrict__ as8, float *__restrict__ score) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    using L = TcSmem<D>;
+    constexpr int KC = L::KC;
+    constexpr uint32_t kTmemCols = (5 * D <= 128) ? 128 : 256;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t n_nodes = n_nodes_dev ? *n_nodes_dev : n_nodes_host;
+    const int64_t n_tiles = (n_nodes + kTcRows - 1) / kTcRows;
+    if ((int64_t)blockIdx.x >= n_tiles) return;  // block-uniform: nothing allocated yet
+
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + L::BAR);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::BAR + 8);
+    float *ws = reinterpret_cast<float *>(smem + L::WS);
+    float *bias = reinterpret_cast<float *>(smem + L::BIAS);
+    const uint32_t smem_base = smem_u32(smem);
+
+    // ---- one-time setup: barrier, TMEM, weights (hi / lo parts, canonical layout) ----
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+    for (int i = tid; i < L::WROWS * KC; i += kTcThreads) {
+        const int row = i / KC, ch = i % KC;  // row: 0..D-1 W_h, D..4D-1 W_ih, 4D..7D-1 W_hh
+        const float *srcw = row < D ? W_h + (size_t)row * D : (row < 4 * D ? W_ih + (size_t)(row - D) * D
+                                                                           : W_hh + (size_t)(row - 4 * D) * D);
+        float4 x = __ldg(reinterpret_cast<const float4 *>(srcw) + ch), hi, lo;
+        split_tf32(x, hi, lo);
+        *reinterpret_cast<float4 *>(smem + L::W_HI + L::off(row, ch)) = hi;
+        *reinterpret_cast<float4 *>(smem + L::W_LO + L::off(row, ch)) = lo;
+    }
+    for (int i = tid; i < 9 * D; i += kTcThreads) {
+        float v = 0.f;
+        if (i < 8 * D) {
+            if (Ws_next) v = Ws_next[i];
+        } else if (W_final) {
+            v = W_final[i - 8 * D];
+        }
+        ws[i] = v;
+    }
+    for (int i = tid; i < 2 * D; i += kTcThreads) bias[i] = b_ih[i] + b_hh[i];
+    for (int i = tid; i < D; i += kTcThreads) {
+        bias[2 * D + i] = b_ih[2 * D + i];
+        bias[3 * D + i] = b_hh[2 * D + i];
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: [0,D) x | [D,2D) r | [2D,3D) z | [3D,4D) i_n | [4D,5D) h_n
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * kTcRows + tid;
+        const bool live = row < n_nodes;
+        // ---- stage this thread's node row: agg and the re-indexed previous state ----
+        {
+            const float4 *pa = reinterpret_cast<const float4 *>(agg + (size_t)(live ? row : 0) * D);
+            int s = -1;
+            if (HAS_H0 && live) s = __ldg(src + row);
+            const float4 *ph = reinterpret_cast<const float4 *>(h_prev + (size_t)(s >= 0 ? s : 0) * D);
+#pragma unroll
+            for (int ch = 0; ch < KC; ++ch) {
+                float4 a = live ? __ldg(pa + ch) : make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
+                split_tf32(a, hi, lo);
+                *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(tid, ch)) = hi;
+                *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(tid, ch)) = lo;
+                if (HAS_H0) {
+                    float4 h = (s >= 0) ? __ldg(ph + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    split_tf32(h, hi, lo);
+                    *reinterpret_cast<float4 *>(smem + L::H_HI + L::off(tid, ch)) = hi;
+                    *reinterpret_cast<float4 *>(smem + L::H_LO + L::off(tid, ch)) = lo;
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- GEMM 1: x = agg . W_h^T  -> TMEM [0, D) ----
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm<D>(smem_base, L::A_HI, L::A_LO, 0, D, tmem_base, false);
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // epilogue 1: x = act(.) back to shared memory (overwrites the agg tile) as hi / lo
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 16) {
+            float v[16];
+            tmem_ld16(t_lane + c0, v);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 x = make_float4(act_apply_tc(v[4 * q], act), act_apply_tc(v[4 * q + 1], act),
+                                       act_apply_tc(v[4 * q + 2], act), act_apply_tc(v[4 * q + 3], act)),
+                       hi, lo;
+                split_tf32(x, hi, lo);
+                *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(tid, c0 / 4 + q)) = hi;
+                *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(tid, c0 / 4 + q)) = lo;
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+
+        // ---- GEMM 2: [r z i_n] = x . W_ih^T ; [r z] += h0 . W_hh[r,z]^T ; h_n = h0 . W_hh[n]^T ----
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm<D>(smem_base, L::A_HI, L::A_LO, D, 3 * D, tmem_base + D, false);
+            if (HAS_H0) {
+                issue_gemm<D>(smem_base, L::H_HI, L::H_LO, 4 * D, 2 * D, tmem_base + D, true);
+                issue_gemm<D>(smem_base, L::H_HI, L::H_LO, 6 * D, D, tmem_base + 4 * D, false);
+            }
+            tc_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // epilogue 2: gates, hidden row, attention projection / score
+        float proj[9];
+#pragma unroll
+        for (int a = 0; a < 9; ++a) proj[a] = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 16) {
+            float vr[16], vz[16], vi[16], vh[16], hn[16];
+            tmem_ld16(t_lane + D + c0, vr);
+            tmem_ld16(t_lane + 2 * D + c0, vz);
+            tmem_ld16(t_lane + 3 * D + c0, vi);
+            if (HAS_H0) tmem_ld16(t_lane + 4 * D + c0, vh);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float h0v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (HAS_H0) {
+                    const float4 hh = *reinterpret_cast<const float4 *>(smem + L::H_HI + L::off(tid, c0 / 4 + q));
+                    const float4 hl = *reinterpret_cast<const float4 *>(smem + L::H_LO + L::off(tid, c0 / 4 + q));
+                    h0v[0] = hh.x + hl.x; h0v[1] = hh.y + hl.y; h0v[2] = hh.z + hl.z; h0v[3] = hh.w + hl.w;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * q + e, c = c0 + j;
+                    const float rg = sigmoid_tc(vr[j] + bias[c]);
+                    const float zg = sigmoid_tc(vz[j] + bias[D + c]);
+                    const float hpart = HAS_H0 ? vh[j] : 0.f;
+                    const float ng = tanhf(vi[j] + bias[2 * D + c] + rg * (hpart + bias[3 * D + c]));
+                    hn[j] = (1.0f - zg) * ng + zg * h0v[e];
+                }
+            }
+            if (live) {
+                float4 *po = reinterpret_cast<float4 *>(hidden + (size_t)row * D + c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) po[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
+            }
+#pragma unroll
+            for (int a = 0; a < 9; ++a) {
+                float s = proj[a];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s = fmaf(hn[j], ws[a * D + c0 + j], s);
+                proj[a] = s;
+            }
+        }
+        if (live) {
+            if (as8) {
+                float4 *po = reinterpret_cast<float4 *>(as8 + (size_t)row * 8);
+                po[0] = make_float4(proj[0], proj[1], proj[2], proj[3]);
+                po[1] = make_float4(proj[4], proj[5], proj[6], proj[7]);
+            }
+            if (score) score[row] = proj[8];
+        }
+        // TMEM reads and shared-memory reads of this tile are done before the next tile overwrites them
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+template <int D, bool HH>
+int launch_node_tc(const float *agg, const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
+                   const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
+                   const float *W_final, int act, int64_t n_nodes, const int64_t *n_nodes_dev, float *hidden,
+                   float *as8, float *score, cudaStream_t st) {
+    constexpr size_t smem = TcSmem<D>::TOTAL;
+    static_assert(smem <= 232448, "tile does not fit the 227 KB shared memory of one CTA");
+    auto kern = k_node_update_tc<D, HH>;
+    RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, n_sm = 148;
+    RG_CUDA_CALL(cudaGetDevice(&dev));
+    RG_CUDA_CALL(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int64_t n_tiles = (n_nodes + kTcRows - 1) / kTcRows;
+    const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);  // persistent: one CTA per SM
+    kern<<<grid, kTcThreads, smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
+                                         n_nodes, n_nodes_dev, hidden, as8, score);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
+
+}  // namespace
+
+// internal entry used by rg_node_update (rg_node.cu); returns RG_ERR_UNSUPPORTED when D has no
+// tensor-core instantiation (the tile must fit 227 KB of shared memory: D <= 48)
+int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
+                      const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
+                      const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
+                      const float *W_final, int32_t act, float *hidden, float *as8, float *score,
+                      cudaStream_t st) {
+#define RG_NODE_TC(DD)                                                                                             \
+    return h_prev ? launch_node_tc<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,  \
+                                             n_nodes, n_nodes_dev, hidden, as8, score, st)                         \
+                  : launch_node_tc<DD, false>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act, \
+                                              n_nodes, n_nodes_dev, hidden, as8, score, st)
+    switch (hidden_dim) {
+        case 16: RG_NODE_TC(16);
+        case 32: RG_NODE_TC(32);
+        case 48: RG_NODE_TC(48);
+        default: return RG_ERR_UNSUPPORTED;
+    }
+#undef RG_NODE_TC
+}
