@@ -285,7 +285,9 @@ def main():
     barrier()
     timing, _lib.Stats.timing = _lib.Stats.timing, None
     edge_ms, edge_bytes = 0.0, 0.0
+    kernel_ms = {}
     for name, meta, a, b in timing:
+        kernel_ms[name] = kernel_ms.get(name, 0.0) + a.elapsed_time(b) / args.steps
         if name != "edge_fwd":
             continue
         seg, d, has_hidden = meta
@@ -348,6 +350,7 @@ def main():
                 "h2d_bytes_per_step": int(batch * 16 + (batch * 8 if args.train else 0)),
                 "d2h_bytes_per_step": int(4 if args.train else batch * loader.n_ent * 4)},
         "gpu_launches": int(launches),
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in kernel_ms.items()},
         "roofline": {"bound": "hbm", "kernel": "k_edge_fwd (fused gather+attention+segmented reduce)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "share_of_step": t_instr / t_dev,

@@ -11,13 +11,15 @@
 //     accuracy (~2^-19 relative) -- plain TF32 would break the 1e-4 parity bound;
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=D/2D/3D, K=8 per
 //     instruction) with fp32 accumulators in TMEM columns [x | r | z | i_n | h_n];
-//   * tcgen05.commit -> mbarrier; all 128 threads (thread t = TMEM lane t = node row t) read their
-//     accumulator row with tcgen05.ld.32x32b, apply the gates, write hidden / as8 / score.
+//   * tcgen05.commit -> mbarrier; 128 x D/16 threads then run the epilogues: warp w owns TMEM lanes
+//     32*(w%4).. (= node rows) and the 16-column slice w/4, read with tcgen05.ld.32x32b.x16, apply
+//     the gates and write hidden; the as8 / score dot products are combined through shared memory.
+//     (Splitting the columns over D/16 warps per lane quarter triples the warps that hide the
+//     staging / epilogue latency; the tile itself stays 128 rows because of the 227 KB budget.)
 #include "rg_common.cuh"
 
 namespace {
 
-constexpr int kTcThreads = 128;
 constexpr int kTcRows = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -132,7 +134,10 @@ __device__ __forceinline__ float act_apply_tc(float v, int act) {
     if (act == 2) return tanhf(v);
     return v;
 }
-__device__ __forceinline__ float sigmoid_tc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// ex2.approx-based forms: relative error ~2^-21, far inside the 1e-4 parity bound, and ~3x fewer
+// instructions than expf / tanhf in the latency-critical epilogue
+__device__ __forceinline__ float sigmoid_tc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_tc(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 // issue the 3xTF32 product  D[tmem_d : N cols] (+)= A(rows 0..127) . B(rows b_row0 .. b_row0+N)^T
 template <int D>
@@ -157,7 +162,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t smem_base, int a_hi, int a_l
 }
 
 template <int D, bool HAS_H0>
-__global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
+__global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
     const float *__restrict__ agg, const float *__restrict__ h_prev, const int32_t *__restrict__ src,
     const float *__restrict__ W_h, const float *__restrict__ W_ih, const float *__restrict__ W_hh,
     const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ Ws_next,
@@ -167,7 +172,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
     using L = TcSmem<D>;
     constexpr int KC = L::KC;
     constexpr uint32_t kTmemCols = (5 * D <= 128) ? 128 : 256;
+    constexpr int kTcThreads = 128 * (D / 16);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int trow = (warp & 3) * 32 + (tid & 31);  // node row of the tile == TMEM lane
+    const int cq = warp >> 2;                       // 16-column slice owned by this thread
     const int64_t n_nodes = n_nodes_dev ? *n_nodes_dev : n_nodes_host;
     const int64_t n_tiles = (n_nodes + kTcRows - 1) / kTcRows;
     if ((int64_t)blockIdx.x >= n_tiles) return;  // block-uniform: nothing allocated yet
@@ -213,29 +221,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // TMEM columns: [0,D) x | [D,2D) r | [2D,3D) z | [3D,4D) i_n | [4D,5D) h_n
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * kTcRows + tid;
+        const int64_t row = tile * kTcRows + trow;
         const bool live = row < n_nodes;
-        // ---- stage this thread's node row: agg and the re-indexed previous state ----
+        // ---- stage this thread's slice of its node row: agg and the re-indexed previous state ----
         {
             const float4 *pa = reinterpret_cast<const float4 *>(agg + (size_t)(live ? row : 0) * D);
             int s = -1;
             if (HAS_H0 && live) s = __ldg(src + row);
             const float4 *ph = reinterpret_cast<const float4 *>(h_prev + (size_t)(s >= 0 ? s : 0) * D);
+            float4 a[4], h[4];
 #pragma unroll
-            for (int ch = 0; ch < KC; ++ch) {
-                float4 a = live ? __ldg(pa + ch) : make_float4(0.f, 0.f, 0.f, 0.f), hi, lo;
-                split_tf32(a, hi, lo);
-                *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(tid, ch)) = hi;
-                *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(tid, ch)) = lo;
+            for (int q = 0; q < 4; ++q) {
+                a[q] = live ? __ldg(pa + 4 * cq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HAS_H0) h[q] = (s >= 0) ? __ldg(ph + 4 * cq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 hi, lo;
+                split_tf32(a[q], hi, lo);
+                *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(trow, 4 * cq + q)) = hi;
+                *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(trow, 4 * cq + q)) = lo;
                 if (HAS_H0) {
-                    float4 h = (s >= 0) ? __ldg(ph + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    split_tf32(h, hi, lo);
-                    *reinterpret_cast<float4 *>(smem + L::H_HI + L::off(tid, ch)) = hi;
-                    *reinterpret_cast<float4 *>(smem + L::H_LO + L::off(tid, ch)) = lo;
+                    split_tf32(h[q], hi, lo);
+                    *reinterpret_cast<float4 *>(smem + L::H_HI + L::off(trow, 4 * cq + q)) = hi;
+                    *reinterpret_cast<float4 *>(smem + L::H_LO + L::off(trow, 4 * cq + q)) = lo;
                 }
             }
         }
@@ -253,8 +266,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
         phase ^= 1;
         tc_fence_after();
         // epilogue 1: x = act(.) back to shared memory (overwrites the agg tile) as hi / lo
-#pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 16) {
+        {
+            const int c0 = 16 * cq;
             float v[16];
             tmem_ld16(t_lane + c0, v);
 #pragma unroll
@@ -263,8 +276,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
                                        act_apply_tc(v[4 * q + 2], act), act_apply_tc(v[4 * q + 3], act)),
                        hi, lo;
                 split_tf32(x, hi, lo);
-                *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(tid, c0 / 4 + q)) = hi;
-                *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(tid, c0 / 4 + q)) = lo;
+                *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(trow, c0 / 4 + q)) = hi;
+                *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(trow, c0 / 4 + q)) = lo;
             }
         }
         fence_proxy_async();
@@ -284,12 +297,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        // epilogue 2: gates, hidden row, attention projection / score
-        float proj[9];
-#pragma unroll
-        for (int a = 0; a < 9; ++a) proj[a] = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 16) {
+        // epilogue 2: gates and the hidden slice; attention projection / score partials
+        {
+            const int c0 = 16 * cq;
             float vr[16], vz[16], vi[16], vh[16], hn[16];
             tmem_ld16(t_lane + D + c0, vr);
             tmem_ld16(t_lane + 2 * D + c0, vz);
@@ -299,8 +309,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
             for (int q = 0; q < 4; ++q) {
                 float h0v[4] = {0.f, 0.f, 0.f, 0.f};
                 if (HAS_H0) {
-                    const float4 hh = *reinterpret_cast<const float4 *>(smem + L::H_HI + L::off(tid, c0 / 4 + q));
-                    const float4 hl = *reinterpret_cast<const float4 *>(smem + L::H_LO + L::off(tid, c0 / 4 + q));
+                    const float4 hh = *reinterpret_cast<const float4 *>(smem + L::H_HI + L::off(trow, c0 / 4 + q));
+                    const float4 hl = *reinterpret_cast<const float4 *>(smem + L::H_LO + L::off(trow, c0 / 4 + q));
                     h0v[0] = hh.x + hl.x; h0v[1] = hh.y + hl.y; h0v[2] = hh.z + hl.z; h0v[3] = hh.w + hl.w;
                 }
 #pragma unroll
@@ -309,7 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
                     const float rg = sigmoid_tc(vr[j] + bias[c]);
                     const float zg = sigmoid_tc(vz[j] + bias[D + c]);
                     const float hpart = HAS_H0 ? vh[j] : 0.f;
-                    const float ng = tanhf(vi[j] + bias[2 * D + c] + rg * (hpart + bias[3 * D + c]));
+                    const float ng = tanh_tc(vi[j] + bias[2 * D + c] + rg * (hpart + bias[3 * D + c]));
                     hn[j] = (1.0f - zg) * ng + zg * h0v[e];
                 }
             }
@@ -318,21 +328,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_node_update_tc(
 #pragma unroll
                 for (int q = 0; q < 4; ++q) po[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
             }
+            if (as8 || score) {
+                // partial dot products over this thread's 16 columns -> shared memory (the x tile is
+                // free: GEMM 2 has completed), summed in slice order by the cq == 0 thread of the row
+                float *part = reinterpret_cast<float *>(smem + L::A_HI) + ((size_t)cq * kTcRows + trow) * 12;
 #pragma unroll
-            for (int a = 0; a < 9; ++a) {
-                float s = proj[a];
+                for (int a = 0; a < 9; ++a) {
+                    float sacc = 0.f;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s = fmaf(hn[j], ws[a * D + c0 + j], s);
-                proj[a] = s;
+                    for (int j = 0; j < 16; ++j) sacc = fmaf(hn[j], ws[a * D + c0 + j], sacc);
+                    part[a] = sacc;
+                }
+                __syncthreads();
+                if (cq == 0 && live) {
+                    float proj[9];
+#pragma unroll
+                    for (int a = 0; a < 9; ++a) {
+                        float sacc = 0.f;
+                        for (int k = 0; k < D / 16; ++k)
+                            sacc += reinterpret_cast<const float *>(smem + L::A_HI)[((size_t)k * kTcRows + trow) * 12 + a];
+                        proj[a] = sacc;
+                    }
+                    if (as8) {
+                        float4 *po = reinterpret_cast<float4 *>(as8 + (size_t)row * 8);
+                        po[0] = make_float4(proj[0], proj[1], proj[2], proj[3]);
+                        po[1] = make_float4(proj[4], proj[5], proj[6], proj[7]);
+                    }
+                    if (score) score[row] = proj[8];
+                }
             }
-        }
-        if (live) {
-            if (as8) {
-                float4 *po = reinterpret_cast<float4 *>(as8 + (size_t)row * 8);
-                po[0] = make_float4(proj[0], proj[1], proj[2], proj[3]);
-                po[1] = make_float4(proj[4], proj[5], proj[6], proj[7]);
-            }
-            if (score) score[row] = proj[8];
         }
         // TMEM reads and shared-memory reads of this tile are done before the next tile overwrites them
         tc_fence_before();
@@ -355,7 +379,7 @@ int launch_node_tc(const float *agg, const float *h_prev, const int32_t *src, co
     RG_CUDA_CALL(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     const int64_t n_tiles = (n_nodes + kTcRows - 1) / kTcRows;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);  // persistent: one CTA per SM
-    kern<<<grid, kTcThreads, smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
+    kern<<<grid, 128 * (D / 16), smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
                                          n_nodes, n_nodes_dev, hidden, as8, score);
     RG_LAUNCH_CHECK();
     return RG_OK;
