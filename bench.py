@@ -35,7 +35,9 @@ WORKLOADS = {  # name -> (synth shape, n_layer, default per-GPU batch)
     "family": ("family", 3, 256),
     "yago310": ("yago310", 5, 8),
     "tiny": ("tiny", 3, 32),
+    "powerlaw": ("powerlaw", 6, 4),      # built from arrays (ArrayLoader): 10 M triples, no text round trip
 }
+ARRAY_WORKLOADS = ("powerlaw",)
 HIDDEN, ATTN = 48, 5
 
 
@@ -118,8 +120,19 @@ def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     from oracle import redgnn_oracle as O
-    task, n_layer, _ = make_dataset(args.workload)
-    data = O.TransductiveData(task)
+    if args.workload in ARRAY_WORKLOADS:
+        from redgnn_b200 import synth
+
+        class _D(object):
+            pass
+        ld = synth.ArrayLoader(WORKLOADS[args.workload][0], seed=0, device="cpu")
+        n_layer = WORKLOADS[args.workload][1]
+        data = _D()
+        data.test_graph = O.Graph(ld._test_graph.triples, ld.n_ent, ld.n_rel)
+        data.test_q, data.n_rel = ld.test_q, ld.n_rel
+    else:
+        task, n_layer, _ = make_dataset(args.workload)
+        data = O.TransductiveData(task)
     sd = O.init_state_dict(n_layer, HIDDEN, ATTN, data.n_rel, seed=1234)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -195,10 +208,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    task, n_layer, batch = make_dataset(args.workload)
+    if args.workload in ARRAY_WORKLOADS:
+        shape, n_layer, batch = WORKLOADS[args.workload]
+        loader, task = synth.ArrayLoader(shape, seed=0, device=dev), None
+    else:
+        task, n_layer, batch = make_dataset(args.workload)
+        with contextlib.redirect_stdout(io.StringIO()):
+            loader = redgnn_b200.TransductiveLoader(task, device=dev)
     batch = args.batch or batch
-    with contextlib.redirect_stdout(io.StringIO()):
-        loader = redgnn_b200.TransductiveLoader(task, device=dev)
     opts = synth.Options(hidden_dim=HIDDEN, attn_dim=ATTN, n_layer=n_layer, n_rel=loader.n_rel, dropout=0.0)
     torch.manual_seed(1234)
     model = redgnn_b200.RED_GNN_trans(opts, loader).to(dev)
@@ -360,7 +377,14 @@ def main():
     }
     if not args.no_cpu_baseline:
         from oracle import redgnn_oracle as O
-        data = O.TransductiveData(task)
+        if task is None:
+            class _D(object):
+                pass
+            data = _D()
+            data.test_graph = O.Graph(loader._test_graph.triples, loader.n_ent, loader.n_rel)
+            data.test_q = loader.test_q
+        else:
+            data = O.TransductiveData(task)
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)

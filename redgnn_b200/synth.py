@@ -90,3 +90,40 @@ class Options(object):
         self.hidden_dim, self.attn_dim, self.n_layer = 48, 5, 3
         self.dropout, self.act, self.n_batch, self.n_tbatch = 0.0, 'relu', 20, 50
         self.__dict__.update(kw)
+
+
+class ArrayLoader(object):
+    """Loader for LARGE synthetic KGs built straight from arrays (no text files, no Python loops):
+    the subset of the DataLoader surface the model and bench.py need (`graph_for`, `n_ent_for`,
+    `n_ent`, `n_rel`, `train_data`, `test_q`).  Row order follows the transductive reference:
+    [facts | inverse facts | self-loops] and [facts | inv | train | inv train | self-loops]."""
+
+    def __init__(self, shape="powerlaw", seed=0, device=None, override=None):
+        import torch
+        from .data import _GraphSlot
+        n_ent, n_rel, n_tri, n_valid, n_test, ah, at, self.n_layer = override or SHAPES[shape]
+        tri = zipf_triples(n_ent, n_rel, n_tri + n_valid + n_test, ah, at, seed)
+        self.n_ent, self.n_rel = n_ent, n_rel
+        self.device = device if device is not None else (
+            torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None)
+        n_fact = n_tri * 3 // 4
+        inv = lambda t: np.stack([t[:, 2], t[:, 1] + n_rel, t[:, 0]], axis=1)
+        dbl = lambda t: np.concatenate([t, inv(t)], axis=0)
+        fact, train, test = tri[:n_fact], tri[n_fact:n_tri], tri[n_tri + n_valid:]
+        self.train_data = dbl(train)
+        self._train_graph = _GraphSlot(dbl(fact), n_ent, n_rel)
+        self._test_graph = _GraphSlot(np.concatenate([dbl(fact), dbl(train)], axis=0), n_ent, n_rel)
+        self.n_fact, self.tn_fact = self._train_graph.n_fact, self._test_graph.n_fact
+        q = np.unique(dbl(test)[:, :2], axis=0)
+        self.test_q = [tuple(x) for x in q.tolist()]
+        self.n_train, self.n_test = len(self.train_data), len(self.test_q)
+
+    def graph_for(self, mode, device=None):
+        slot = self._train_graph if mode == 'train' else self._test_graph
+        return slot.on(device if device is not None else self.device)
+
+    def n_ent_for(self, mode):
+        return self.n_ent
+
+    def get_neighbors(self, nodes, mode='train'):
+        return self.graph_for(mode).get_neighbors(nodes)
