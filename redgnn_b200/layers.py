@@ -132,6 +132,7 @@ class RedGNN(torch.nn.Module):
     # once into a CUDA graph and replayed: the ~100 launches / allocations of a forward cost one
     # cudaGraphLaunch instead of milliseconds of host time.
     use_cuda_graph = True
+    inference_in_eval = True
     MAX_CACHED_GRAPHS = 4
 
     def _run_graph(self, q_sub, q_rel, graph, n_ent_out):
@@ -211,7 +212,10 @@ class RedGNN(torch.nn.Module):
             if len(s) and (s.min() < 0 or s.max() >= graph.n_ent):
                 raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % graph.n_ent)
         q_sub, q_rel = self._to_device(subs, dev), self._to_device(rels, dev)
-        need_grad = torch.is_grad_enabled()
+        # eval(): the reference's evaluate() never differentiates (base_model.py:106 takes .data), so an
+        # eval-mode forward runs the inference kernels and returns a tensor WITHOUT autograd history
+        # unless `inference_in_eval` is switched off; train() mode always keeps autograd.
+        need_grad = torch.is_grad_enabled() and (self.training or not self.inference_in_eval)
         if not need_grad and not (self.training and self.dropout.p > 0) and n > 0 \
                 and n * graph.n_ent * (d + 10) * 4 * 4 <= self.ASYNC_BUDGET_BYTES:
             if self.use_cuda_graph and _lib.Stats.timing is None:

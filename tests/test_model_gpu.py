@@ -23,6 +23,7 @@ def oracle_loss_grads(sd, graph, tri, n_layer, act):
 
 
 def cuda_loss_backward(model, tri):
+    model.inference_in_eval = False            # differentiate through an eval-mode (dropout-free) forward
     out = model(tri[:, 0], tri[:, 1])
     pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
     mx = out.max(1, keepdim=True)[0]
@@ -66,6 +67,7 @@ def test_golden_family_scores_ranks_grads(tmp_path):
         assert round(a, 3) == round(b, 3)
     tri = fx["train_triples"]
     model.zero_grad()
+    model.inference_in_eval = False
     out = model(tri[:, 0], tri[:, 1])                     # mode='train' graph, eval() => no dropout
     pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
     mx = out.max(1, keepdim=True)[0]
@@ -169,6 +171,7 @@ def test_golden_fb237_v2_scores(tmp_path):
                         fx["eval_filters"].astype(np.float64))
     assert np.array_equal(np.array(ranks), fx["eval_ranks"])
     tri = fx["train_triples"]
+    model.inference_in_eval = False
     out = model(tri[:, 0], tri[:, 1])
     pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
     mx = out.max(1, keepdim=True)[0]
@@ -199,7 +202,12 @@ def test_fused_inference_path_vs_oracle(tiny_dir, act, d, a, n_layer):
     want = O.model_forward(sd, D.test_graph, subs, rels, n_layer, act)
     assert_close(got, want, 1e-4, "fused scores")
     assert torch.equal(got.cpu() == 0, want == 0)
-    assert_close(got, model(subs, rels, mode="test"), 1e-5, "fused vs torch-composed path")
+    model.inference_in_eval = False
+    composed = model(subs, rels, mode="test")
+    model.inference_in_eval = True
+    assert composed.grad_fn is not None and got.grad_fn is None
+    assert_close(got, composed, 1e-5, "fused vs torch-composed path")
+    assert model(subs, rels, mode="test").grad_fn is None      # eval(): inference kernels by default
     with torch.no_grad():
         assert torch.equal(got, model(subs, rels, mode="test")), "inference must be bit-reproducible"
 
