@@ -76,6 +76,8 @@ typedef struct rg_frontier {
     int32_t n_ent;
     uint32_t *emask;         /* [n_ent][Wn]                                                   */
     uint32_t *dict;          /* [n_query][We][2]                                              */
+    int32_t *qinfo;          /* optional [n_query][2] = {rank of the query's first node, node count};
+                                count == n_ent marks a COMPLETE frontier (rank = base + entity)    */
 } rg_frontier;
 
 /* Segment description for the fused edge kernels.
@@ -97,6 +99,9 @@ typedef struct rg_segments {
     const int32_t *seg_ent;        /* implicit: [n_seg]                                        */
     const int32_t *ent_ptr;        /* implicit: [n_ent+1]                                      */
     const uint32_t *peer_dict;     /* implicit: [n_query][We][2]                               */
+    const int32_t *peer_qinfo;     /* implicit, optional: rg_frontier.qinfo of the peer frontier     */
+    int32_t n_table_rows;          /* rows of the relation tables (2R+1); > 0 lets the forward kernel
+                                      stage rela / ar8 in shared memory when they fit            */
 } rg_segments;
 
 /* Queue for segments longer than RG_HEAVY_CHUNK candidate slots: they are cut into chunks that

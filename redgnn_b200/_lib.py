@@ -24,13 +24,14 @@ class RgGraph(C.Structure):
 
 class RgFrontier(C.Structure):
     _fields_ = [("n_query", C.c_int32), ("n_ent", C.c_int32),
-                ("emask", C.c_void_p), ("dict", C.c_void_p)]
+                ("emask", C.c_void_p), ("dict", C.c_void_p), ("qinfo", C.c_void_p)]
 
 
 class RgSegments(C.Structure):
     _fields_ = [("mode", C.c_int32), ("n_ent", C.c_int32), ("n_seg", C.c_int64), ("n_seg_dev", C.c_void_p),
                 ("seg_query", C.c_void_p), ("seg_ptr", C.c_void_p), ("adj", C.c_void_p),
-                ("seg_ent", C.c_void_p), ("ent_ptr", C.c_void_p), ("peer_dict", C.c_void_p)]
+                ("seg_ent", C.c_void_p), ("ent_ptr", C.c_void_p), ("peer_dict", C.c_void_p),
+                ("peer_qinfo", C.c_void_p), ("n_table_rows", C.c_int32)]
 
 
 class RgHeavy(C.Structure):

@@ -9,6 +9,8 @@
 // sum is a fixed function of the slot order (no atomics) => bit-reproducible.
 // Segments longer than RG_HEAVY_CHUNK slots are cut into chunks via a device queue; chunk partials
 // are added back in chunk order by a fix-up kernel.
+#include <algorithm>
+
 #include "rg_common.cuh"
 
 namespace {
@@ -25,9 +27,11 @@ struct Slot {
     bool active;
 };
 
-// probe candidate slot `slot` of the segment of query q
+// probe candidate slot `slot` of the segment of query q.  complete_base >= 0: the peer frontier of
+// this query holds every entity, so rank = base + entity and no dictionary probe is needed.
 template <bool IMPLICIT>
-__device__ __forceinline__ Slot probe_slot(const rg_segments &S, const uint2 *drow, int slot, bool valid) {
+__device__ __forceinline__ Slot probe_slot(const rg_segments &S, const uint2 *drow, int complete_base, int slot,
+                                           bool valid) {
     Slot s;
     s.peer = 0;
     s.rel = 0;
@@ -36,16 +40,29 @@ __device__ __forceinline__ Slot probe_slot(const rg_segments &S, const uint2 *dr
         int2 pr = __ldg(reinterpret_cast<const int2 *>(S.adj) + slot);
         s.rel = pr.y;
         if (IMPLICIT) {
-            uint2 d = __ldg(drow + (pr.x >> 5));
-            uint32_t bit = 1u << (pr.x & 31);
-            s.active = (d.x & bit) != 0u;
-            s.peer = (int)(d.y + __popc(d.x & (bit - 1u)));
+            if (complete_base >= 0) {
+                s.active = true;
+                s.peer = complete_base + pr.x;
+            } else {
+                uint2 d = __ldg(drow + (pr.x >> 5));
+                uint32_t bit = 1u << (pr.x & 31);
+                s.active = (d.x & bit) != 0u;
+                s.peer = (int)(d.y + __popc(d.x & (bit - 1u)));
+            }
         } else {
             s.peer = pr.x;
             s.active = true;
         }
     }
     return s;
+}
+
+// warp-uniform: rank base of query q if its peer frontier is complete, else -1
+template <bool IMPLICIT>
+__device__ __forceinline__ int complete_base_of(const rg_segments &S, int q) {
+    if (!IMPLICIT || S.peer_qinfo == nullptr) return -1;
+    const int2 qi = __ldg(reinterpret_cast<const int2 *>(S.peer_qinfo) + q);
+    return qi.y == S.n_ent ? qi.x : -1;
 }
 
 struct SegRange {
@@ -96,12 +113,13 @@ __device__ __forceinline__ void enqueue_heavy(const rg_heavy &H, int64_t seg, in
 // forward: acc = sum over active slots in [lo, hi) of alpha * (hidden[peer] + rela[rel])
 // On return lanes 0..3 hold the reduced row pieces (float4 index v*4 + lane).
 // ------------------------------------------------------------------------------------------
-template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+template <int D, bool HAS_HIDDEN, bool IMPLICIT, bool SMEM_TAB = false>
 __device__ __forceinline__ void fwd_range(const rg_segments &S, int q, int lo, int hi,
                                           const float *__restrict__ hidden, const float *__restrict__ as8,
                                           const float *__restrict__ rela, const float *__restrict__ ar8,
                                           const float *__restrict__ aq8, const float *__restrict__ w8,
-                                          float b_alpha, float4 (&acc)[D / 16]) {
+                                          float b_alpha, float4 (&acc)[D / 16], const float *s_rela = nullptr,
+                                          const float *s_ar8 = nullptr) {
     constexpr int NV = D / 16;
     const int lane = threadIdx.x & 31, grp = lane >> 2, ql = lane & 3;
     const float2 aq2 = __ldg(reinterpret_cast<const float2 *>(aq8 + (size_t)q * 8) + ql);
@@ -110,10 +128,11 @@ __device__ __forceinline__ void fwd_range(const rg_segments &S, int q, int lo, i
                                  : nullptr;
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cbase = complete_base_of<IMPLICIT>(S, q);
 
     for (int base = lo; base < hi; base += 32) {
         const int slot = base + lane;
-        Slot s = probe_slot<IMPLICIT>(S, drow, slot, slot < hi);
+        Slot s = probe_slot<IMPLICIT>(S, drow, cbase, slot, slot < hi);
         const unsigned m = __ballot_sync(RG_FULL_MASK, s.active);
         const int cnt = __popc(m);
         for (int it = 0; it < cnt; it += 8) {
@@ -125,8 +144,11 @@ __device__ __forceinline__ void fwd_range(const rg_segments &S, int q, int lo, i
             float4 x[NV];
             float part = 0.f;
             if (on) {
-                const float4 *rp = reinterpret_cast<const float4 *>(rela + (size_t)r * D);
-                float2 z = __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
+                // relation row / attention row: shared-memory copies when staged (LDS), else global
+                const float4 *rp = SMEM_TAB ? reinterpret_cast<const float4 *>(s_rela + r * D)
+                                            : reinterpret_cast<const float4 *>(rela + (size_t)r * D);
+                float2 z = SMEM_TAB ? reinterpret_cast<const float2 *>(s_ar8 + r * 8)[ql]
+                                    : __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
                 if (HAS_HIDDEN) {
                     const float4 *hp = reinterpret_cast<const float4 *>(hidden + (size_t)p * D);
                     float4 h[NV];
@@ -135,14 +157,14 @@ __device__ __forceinline__ void fwd_range(const rg_segments &S, int q, int lo, i
                     float2 a = __ldg(reinterpret_cast<const float2 *>(as8 + (size_t)p * 8) + ql);
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        float4 t = ldg4(rp + v * 4 + ql);
+                        float4 t = SMEM_TAB ? rp[v * 4 + ql] : ldg4(rp + v * 4 + ql);
                         x[v] = make_float4(h[v].x + t.x, h[v].y + t.y, h[v].z + t.z, h[v].w + t.w);
                     }
                     z.x += a.x;
                     z.y += a.y;
                 } else {
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) x[v] = ldg4(rp + v * 4 + ql);
+                    for (int v = 0; v < NV; ++v) x[v] = SMEM_TAB ? rp[v * 4 + ql] : ldg4(rp + v * 4 + ql);
                 }
                 z.x += aq2.x;
                 z.y += aq2.y;
@@ -185,7 +207,7 @@ __device__ __forceinline__ void store_row(float *dst, const float4 (&acc)[D / 16
 }
 
 template <int D, bool HAS_HIDDEN, bool IMPLICIT>
-__global__ void __launch_bounds__(kBlock) k_edge_fwd(rg_segments S, const float *__restrict__ hidden,
+__global__ void __launch_bounds__(kBlock, 5) k_edge_fwd(rg_segments S, const float *__restrict__ hidden,
                                                      const float *__restrict__ as8, const float *__restrict__ rela,
                                                      const float *__restrict__ ar8, const float *__restrict__ aq8,
                                                      const float *__restrict__ w8, const float *__restrict__ b_alpha,
@@ -202,6 +224,47 @@ __global__ void __launch_bounds__(kBlock) k_edge_fwd(rg_segments S, const float 
     float4 acc[D / 16];
     fwd_range<D, HAS_HIDDEN, IMPLICIT>(S, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), acc);
     store_row<D>(agg + (size_t)seg * D, acc, lane);
+}
+
+// Persistent variant for the implicit (model) path: 16 warps per CTA, CTAs sized to the SM count,
+// the relation tables (rela [rows][D], ar8 [rows][8]) staged once per CTA in shared memory so the
+// per-edge relation row comes from LDS (half the L1 wavefronts of the global path), segments
+// handed out round-robin (warp w of CTA c takes c*16+w, then += grid*16).
+constexpr int kPWarps = 16;
+
+template <int D, bool HAS_HIDDEN>
+__global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, const float *__restrict__ hidden,
+                                                               const float *__restrict__ as8,
+                                                               const float *__restrict__ rela,
+                                                               const float *__restrict__ ar8,
+                                                               const float *__restrict__ aq8,
+                                                               const float *__restrict__ w8,
+                                                               const float *__restrict__ b_alpha,
+                                                               float *__restrict__ agg, rg_heavy H, int has_heavy) {
+    extern __shared__ __align__(16) float s_tab[];
+    const int rows = S.n_table_rows;
+    float *s_rela = s_tab, *s_ar8 = s_tab + (size_t)rows * D;
+    for (int i = threadIdx.x; i < rows * D / 4; i += kPWarps * 32)
+        reinterpret_cast<float4 *>(s_rela)[i] = __ldg(reinterpret_cast<const float4 *>(rela) + i);
+    for (int i = threadIdx.x; i < rows * 2; i += kPWarps * 32)
+        reinterpret_cast<float4 *>(s_ar8)[i] = __ldg(reinterpret_cast<const float4 *>(ar8) + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
+    const float ba = __ldg(b_alpha);
+    for (int64_t seg = (int64_t)blockIdx.x * kPWarps + (threadIdx.x >> 5); seg < n_true;
+         seg += (int64_t)gridDim.x * kPWarps) {
+        SegRange r = seg_range<true>(S, seg);
+        int hi = r.hi;
+        if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
+            enqueue_heavy(H, seg, r.hi - r.lo, lane);
+            hi = r.lo + RG_HEAVY_CHUNK;
+        }
+        float4 acc[D / 16];
+        fwd_range<D, HAS_HIDDEN, true, true>(S, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, acc, s_rela,
+                                             s_ar8);
+        store_row<D>(agg + (size_t)seg * D, acc, lane);
+    }
 }
 
 template <int D, bool HAS_HIDDEN, bool IMPLICIT>
@@ -290,10 +353,11 @@ __device__ __forceinline__ void bwd_range(const rg_segments &S, int64_t seg, int
     sm.z = make_float2(0.f, 0.f);
     sm.wz = make_float2(0.f, 0.f);
     sm.gl = 0.f;
+    const int cbase = complete_base_of<IMPLICIT>(S, q);
 
     for (int base = lo; base < hi; base += 32) {
         const int slot = base + lane;
-        Slot s = probe_slot<IMPLICIT>(S, drow, slot, slot < hi);
+        Slot s = probe_slot<IMPLICIT>(S, drow, cbase, slot, slot < hi);
         const unsigned m = __ballot_sync(RG_FULL_MASK, s.active);
         const int cnt = __popc(m);
         for (int it = 0; it < cnt; it += 8) {
@@ -465,9 +529,33 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
     const int has_heavy = heavy && heavy->max_chunks > 0 && heavy->max_nodes > 0;
     if (has_heavy) H = *heavy;
     if (seg->n_seg == 0) return RG_OK;
-    const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
-    k_edge_fwd<D, HH, IM><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, agg, H, has_heavy);
-    RG_LAUNCH_CHECK();
+    const size_t tab_bytes = (size_t)seg->n_table_rows * (D + 8) * sizeof(float);
+    bool persistent = false;
+    if constexpr (IM) {
+        // relation tables staged in shared memory when two 16-warp CTAs still fit one SM
+        if (seg->n_table_rows > 0 && tab_bytes <= 110 * 1024 && seg->n_seg >= 4096) {
+            auto kern = k_edge_fwd_p<D, HH>;
+            RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+            int dev = 0, n_sm = 148, per_sm = 1;
+            RG_CUDA_CALL(cudaGetDevice(&dev));
+            RG_CUDA_CALL(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            RG_CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPWarps * 32, tab_bytes));
+            if (per_sm >= 1) {
+                const int64_t want = rg_cdiv(seg->n_seg, kPWarps);
+                const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)n_sm * per_sm);
+                kern<<<grid, kPWarps * 32, tab_bytes, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, agg, H,
+                                                            has_heavy);
+                RG_LAUNCH_CHECK();
+                persistent = true;
+            }
+        }
+    }
+    if (!persistent) {
+        const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
+        k_edge_fwd<D, HH, IM><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, agg, H,
+                                                       has_heavy);
+        RG_LAUNCH_CHECK();
+    }
     if (has_heavy) {
         k_edge_fwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, H);
         RG_LAUNCH_CHECK();

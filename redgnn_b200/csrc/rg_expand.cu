@@ -263,6 +263,18 @@ __global__ void __launch_bounds__(kBlock) k_emit_edges(const int32_t *__restrict
     }
 }
 
+// per query: {rank of its first node, number of its nodes}; a query whose count equals n_ent has a
+// COMPLETE frontier: rank(b, e) = base + e and every candidate edge is active (no dictionary probe)
+__global__ void __launch_bounds__(kBlock) k_query_info(const uint32_t *__restrict__ dict, int n_query, int We,
+                                                       const int64_t *__restrict__ total, int32_t *qinfo) {
+    int q = blockIdx.x * kBlock + threadIdx.x;
+    if (q >= n_query) return;
+    uint32_t base = dict[((size_t)q * We) * 2 + 1];
+    uint32_t next = (q + 1 < n_query) ? dict[((size_t)(q + 1) * We) * 2 + 1] : (uint32_t)*total;
+    qinfo[2 * q] = (int32_t)base;
+    qinfo[2 * q + 1] = (int32_t)(next - base);
+}
+
 int check_frontier(const rg_frontier *fr) {
     if (!fr || !fr->emask || !fr->dict || fr->n_query <= 0 || fr->n_ent <= 0) return RG_ERR_BAD_ARG;
     if ((int64_t)fr->n_query * fr->n_ent >= (int64_t)INT32_MAX) return RG_ERR_TOO_LARGE;
@@ -279,6 +291,12 @@ int dict_prefix(const rg_frontier *fr, const RgWorkspace &w, int64_t *count_out,
     RG_LAUNCH_CHECK();
     k_dict_apply<<<(unsigned)nb, kBlock, 0, st>>>(fr->dict, n_words, w.dict_blockprefix);
     RG_LAUNCH_CHECK();
+    if (fr->qinfo) {
+        k_query_info<<<(unsigned)rg_cdiv(fr->n_query, kBlock), kBlock, 0, st>>>(fr->dict, fr->n_query,
+                                                                               rg_words_ent(fr->n_ent), count_out,
+                                                                               fr->qinfo);
+        RG_LAUNCH_CHECK();
+    }
     return RG_OK;
 }
 

@@ -80,7 +80,7 @@ class DeviceGraph(object):
         ws = self.workspace(n_query)
         check(lib.rg_frontier_from_nodes(ptr(nodes64), nodes64.shape[0], C.byref(fr.c_struct()), ptr(fr.counts),
                                          ptr(ws), ws.numel(), stream_ptr()))
-        _lib.Stats.launches += 4      # k_set_nodes + dict reduce / scan / apply
+        _lib.Stats.launches += 5      # k_set_nodes + dict reduce / scan / apply + query info
         return fr
 
     def step(self, fr_in):
@@ -90,7 +90,7 @@ class DeviceGraph(object):
         ws = self.workspace(fr_in.n_query)
         check(lib.rg_frontier_step(C.byref(self.c_struct()), C.byref(fr_in.c_struct()), C.byref(fr_out.c_struct()),
                                    ptr(fr_out.counts), ptr(ws), ws.numel(), stream_ptr()))
-        _lib.Stats.launches += 6      # fact_count, scan, transpose, dict reduce / scan / apply
+        _lib.Stats.launches += 7      # fact_count, scan, transpose, dict reduce / scan / apply, query info
         return fr_out
 
     def emit_edges(self, fr_in, fr_out, n_edges):
@@ -133,13 +133,15 @@ class Frontier(object):
         self.emask = torch.empty(lib.rg_frontier_emask_bytes(n_query, n_ent) // 4, dtype=torch.int32, device=device)
         self.dict = torch.empty(lib.rg_frontier_dict_bytes(n_query, n_ent) // 4, dtype=torch.int32, device=device)
         self.counts = torch.zeros(_lib.RG_COUNTS_WORDS, dtype=torch.int64, device=device)
+        self.qinfo = torch.empty(2 * n_query, dtype=torch.int32, device=device)
         self.n_nodes = None      # host copies of the hop counts, filled by read_counts() / RedGNN.last_stats
         self.n_edges = None
         self._c = None
 
     def c_struct(self):
         if self._c is None:
-            self._c = _lib.RgFrontier(self.n_query, self.n_ent, self.emask.data_ptr(), self.dict.data_ptr())
+            self._c = _lib.RgFrontier(self.n_query, self.n_ent, self.emask.data_ptr(), self.dict.data_ptr(),
+                                      self.qinfo.data_ptr())
         return self._c
 
     def read_counts(self, also=None):

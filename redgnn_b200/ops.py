@@ -23,6 +23,8 @@ class Segments(object):
         self.heavy_bound = (int(heavy_bound[0]), int(heavy_bound[1]))   # (max_chunks, max_nodes)
         self.n_edges = int(adj.shape[0]) if mode == 0 else None       # implicit: set by the caller if known
         self.n_seg_dev = None      # optional int64 device scalar: true segment count (n_seg = upper bound)
+        self.peer_qinfo = None     # implicit: per-query {base, count} of the peer frontier
+        self.n_table_rows = 0      # 2R+1 when known: lets the forward kernel stage rela / ar8 in smem
         self._c = None
 
     @staticmethod
@@ -30,9 +32,11 @@ class Segments(object):
         """Segments = nodes (node_b[i], node_e[i]); edges pulled from the CSR row of node_e[i] and
         filtered / ranked through `peer_frontier`'s dictionary."""
         n_query = peer_frontier.n_query
-        return Segments(1, node_b.shape[0], node_b, ent_adj, n_ent=peer_frontier.n_ent, seg_ent=node_e,
-                        ent_ptr=ent_ptr, peer_dict=peer_frontier.dict,
-                        heavy_bound=(heavy_per_query[0] * n_query, heavy_per_query[1] * n_query))
+        seg = Segments(1, node_b.shape[0], node_b, ent_adj, n_ent=peer_frontier.n_ent, seg_ent=node_e,
+                       ent_ptr=ent_ptr, peer_dict=peer_frontier.dict,
+                       heavy_bound=(heavy_per_query[0] * n_query, heavy_per_query[1] * n_query))
+        seg.peer_qinfo = peer_frontier.qinfo
+        return seg
 
     @staticmethod
     def explicit(seg_index, peer_index, rel, query, n_seg):
@@ -61,7 +65,9 @@ class Segments(object):
                                       self.adj.data_ptr(),
                                       self.seg_ent.data_ptr() if self.seg_ent is not None else None,
                                       self.ent_ptr.data_ptr() if self.ent_ptr is not None else None,
-                                      self.peer_dict.data_ptr() if self.peer_dict is not None else None)
+                                      self.peer_dict.data_ptr() if self.peer_dict is not None else None,
+                                      self.peer_qinfo.data_ptr() if self.peer_qinfo is not None else None,
+                                      self.n_table_rows)
         return self._c
 
 
@@ -92,6 +98,8 @@ def edge_agg_forward(fwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha):
     """Raw launcher (no autograd): returns agg [n_seg, D]."""
     _lib.require_cuda(rela, ar8, aq8, w8, b_alpha, hidden, as8)
     d = rela.shape[1]
+    if fwd_seg.n_table_rows != rela.shape[0]:
+        fwd_seg.n_table_rows, fwd_seg._c = rela.shape[0], None
     agg = torch.empty((fwd_seg.n_seg, d), dtype=torch.float32, device=rela.device)
     heavy = _Heavy(fwd_seg.heavy_bound, d, rela.device)
     with _lib.Stats.timed("edge_fwd", (fwd_seg, d, hidden is not None)):

@@ -44,15 +44,15 @@ def test_version_sizes_and_errors_without_gpu():
     assert lib.rg_frontier_nodes(None, None, None, None, None) == -1
     assert lib.rg_edge_agg_fwd(None, 48, *([None] * 8), None, None) == -1
     assert lib.rg_scatter_scores(5, None, None, None, None, 3, None, None) == -1
-    fr = _lib.RgFrontier(70000, 70000, 1, 1)
+    fr = _lib.RgFrontier(70000, 70000, 1, 1, None)
     assert lib.rg_frontier_nodes(ctypes.byref(fr), None, None, None, None) == -4
 
 
 def test_struct_layout_matches_header():
     from redgnn_b200 import _lib
     assert ctypes.sizeof(_lib.RgGraph) == 16 + 7 * 8
-    assert ctypes.sizeof(_lib.RgFrontier) == 8 + 2 * 8
-    assert ctypes.sizeof(_lib.RgSegments) == 16 + 7 * 8
+    assert ctypes.sizeof(_lib.RgFrontier) == 8 + 3 * 8
+    assert ctypes.sizeof(_lib.RgSegments) == 16 + 8 * 8 + 8
     assert ctypes.sizeof(_lib.RgHeavy) == 8 + 7 * 8
 
 
