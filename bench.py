@@ -82,7 +82,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -357,6 +357,13 @@ def main():
         return
 
     peak, peak_src = peaks()
+    traffic = None                                   # DRAM bytes per launch from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "edge_fwd_traffic.json")
+    if os.path.isfile(tpath) and not args.train:
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("workload") == args.workload:
+            traffic = tj["traffic_bytes_per_launch"]
     qps = world * batch * args.steps / t_dev
     achieved = (edge_bytes / 1e9) / (edge_ms * 1e-3) if edge_ms > 0 else 0.0
     line = {
@@ -375,7 +382,7 @@ def main():
         "kernel_ms_per_step": {k: round(v, 4) for k, v in kernel_ms.items()},
         "roofline": {"bound": "hbm", "kernel": "k_edge_fwd (fused gather+attention+segmented reduce)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "share_of_step": t_instr / t_dev,
+                     "traffic": traffic, "peak_source": peak_src, "share_of_step": t_instr / t_dev,
                      "timing": "CUDA events around every rg_edge_agg_fwd launch, instrumented pass over the same batches",
                      "bytes_model": "(16+4d)*E + 4d*N' per launch (16*E + 4d*N' at layer 0)"},
         "clocks": clocks,
