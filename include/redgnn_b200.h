@@ -198,6 +198,19 @@ int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_d
                    const float *b_ih, const float *b_hh, const float *Ws_next, const float *W_final,
                    int32_t act, float *hidden, float *as8, float *score, void *stream);
 
+/* Training forward of the same node update (tensor-core kernel, hidden_dim <= 48): applies the
+ * caller's dropout mask (models.py:82; values 0 or 1/(1-p), NULL = no dropout) between act(W_h agg)
+ * and the GRU and writes saved[6][n][D] = {act(W_h agg), r, z, n, W_hn h0 + b_hn, h0} for the
+ * backward pass.  rg_gru_bwd_elem is the elementwise part of that backward:
+ *   g_gi[n][3D], g_gh[n][3D] = gradients of the GRU pre-activations (r, z, n) on the input / hidden
+ *   side, g_h0_direct[n][D] = g_hidden * z; the GEMMs around it are plain library calls. */
+int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const float *agg, const float *h_prev,
+                         const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
+                         const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
+                         float *hidden, float *saved, void *stream);
+int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const float *g_hidden, const float *saved,
+                    float *g_gi, float *g_gh, float *g_h0_direct, void *stream);
+
 /* scores_all[node_b[j]][node_e[j]] = score[j] for j < n (models.py:87-88; scores_all is zeroed by
  * the caller, so unvisited entities keep an exact 0). */
 int rg_scatter_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,

@@ -266,7 +266,56 @@ extern "C" int rg_scatter_scores(int64_t n_nodes, const int64_t *n_nodes_dev, co
 int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
                       const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                       const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
-                      const float *W_final, int32_t act, float *hidden, float *as8, float *score, cudaStream_t st);
+                      const float *W_final, int32_t act, float *hidden, float *as8, float *score,
+                      const float *drop_mask, float *saved, cudaStream_t st);
+
+// elementwise part of the GRU-cell backward (the GEMMs around it are plain library calls)
+__global__ void __launch_bounds__(256) k_gru_bwd_elem(int64_t n_elem, int D, const float *__restrict__ g_h,
+                                                      const float *__restrict__ saved, float *__restrict__ g_gi,
+                                                      float *__restrict__ g_gh, float *__restrict__ g_h0d) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_elem) return;
+    const int64_t node = i / D;
+    const int c = (int)(i % D);
+    const float r = saved[n_elem + i], z = saved[2 * n_elem + i], nn = saved[3 * n_elem + i];
+    const float hl = saved[4 * n_elem + i], h0 = saved[5 * n_elem + i], g = g_h[i];
+    const float g_np = g * (1.f - z) * (1.f - nn * nn);   // d/d(pre-activation of n)
+    const float g_zp = g * (h0 - nn) * z * (1.f - z);
+    const float g_rp = g_np * hl * r * (1.f - r);
+    float *gi = g_gi + node * 3 * D, *gh = g_gh + node * 3 * D;
+    gi[c] = g_rp;
+    gi[D + c] = g_zp;
+    gi[2 * D + c] = g_np;
+    gh[c] = g_rp;
+    gh[D + c] = g_zp;
+    gh[2 * D + c] = g_np * r;
+    g_h0d[i] = g * z;
+}
+
+extern "C" int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const float *g_hidden, const float *saved,
+                               float *g_gi, float *g_gh, float *g_h0_direct, void *stream) {
+    if (n_nodes < 0 || hidden_dim <= 0 || !g_hidden || !saved || !g_gi || !g_gh || !g_h0_direct) return RG_ERR_BAD_ARG;
+    if (n_nodes == 0) return RG_OK;
+    const int64_t n_elem = n_nodes * hidden_dim;
+    k_gru_bwd_elem<<<(unsigned)rg_cdiv(n_elem, 256), 256, 0, (cudaStream_t)stream>>>(n_elem, hidden_dim, g_hidden,
+                                                                                  saved, g_gi, g_gh, g_h0_direct);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
+
+// training forward: tensor-core kernel only (hidden_dim <= 48); also writes saved[6][n][D] =
+// {act(W_h agg) before dropout, r, z, n, W_hn h0 + b_hn, h0} for the backward pass
+extern "C" int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const float *agg, const float *h_prev,
+                                    const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
+                                    const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
+                                    float *hidden, float *saved, void *stream) {
+    if (n_nodes < 0 || !agg || !W_h || !W_ih || !W_hh || !b_ih || !b_hh || !hidden || !saved) return RG_ERR_BAD_ARG;
+    if ((h_prev == nullptr) != (src == nullptr) || act < 0 || act > 2) return RG_ERR_BAD_ARG;
+    if (hidden_dim > 48) return RG_ERR_UNSUPPORTED;
+    if (n_nodes == 0) return RG_OK;
+    return rg_node_update_tc(hidden_dim, n_nodes, nullptr, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, nullptr,
+                             nullptr, act, hidden, nullptr, nullptr, drop_mask, saved, (cudaStream_t)stream);
+}
 
 extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
                               const float *h_prev,
@@ -284,7 +333,7 @@ extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t
     const char *force_simt = std::getenv("REDGNN_NODE_SIMT");
     if (hidden_dim <= 48 && !(force_simt && force_simt[0] == '1'))
         return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh,
-                                 Ws_next, W_final, act, hidden, as8, score, st);
+                                 Ws_next, W_final, act, hidden, as8, score, nullptr, nullptr, st);
 #define RG_NODE(DD)                                                                                              \
     return h_prev ? launch_node<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,   \
                                           n_nodes, n_nodes_dev, hidden, as8, score, st)                                       \

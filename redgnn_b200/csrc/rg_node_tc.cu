@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
     const float *__restrict__ W_h, const float *__restrict__ W_ih, const float *__restrict__ W_hh,
     const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ Ws_next,
     const float *__restrict__ W_final, int act, int64_t n_nodes_host, const int64_t *__restrict__ n_nodes_dev,
-    float *__restrict__ hidden, float *__restrict__ as8, float *__restrict__ score) {
+    float *__restrict__ hidden, float *__restrict__ as8, float *__restrict__ score,
+    const float *__restrict__ drop_mask, float *__restrict__ saved) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using L = TcSmem<D>;
     constexpr int KC = L::KC;
@@ -275,6 +276,14 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                 float4 x = make_float4(act_apply_tc(v[4 * q], act), act_apply_tc(v[4 * q + 1], act),
                                        act_apply_tc(v[4 * q + 2], act), act_apply_tc(v[4 * q + 3], act)),
                        hi, lo;
+                if (live) {  // training: keep x_act for the backward pass, apply the (scaled) dropout mask
+                    const size_t o = (size_t)row * D + c0 + 4 * q;
+                    if (saved) *reinterpret_cast<float4 *>(saved + o) = x;
+                    if (drop_mask) {
+                        const float4 mk = __ldg(reinterpret_cast<const float4 *>(drop_mask + o));
+                        x = make_float4(x.x * mk.x, x.y * mk.y, x.z * mk.z, x.w * mk.w);
+                    }
+                }
                 split_tf32(x, hi, lo);
                 *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(trow, c0 / 4 + q)) = hi;
                 *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(trow, c0 / 4 + q)) = lo;
@@ -318,9 +327,17 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                     const int j = 4 * q + e, c = c0 + j;
                     const float rg = sigmoid_tc(vr[j] + bias[c]);
                     const float zg = sigmoid_tc(vz[j] + bias[D + c]);
-                    const float hpart = HAS_H0 ? vh[j] : 0.f;
-                    const float ng = tanh_tc(vi[j] + bias[2 * D + c] + rg * (hpart + bias[3 * D + c]));
+                    const float hlin = (HAS_H0 ? vh[j] : 0.f) + bias[3 * D + c];
+                    const float ng = tanh_tc(vi[j] + bias[2 * D + c] + rg * hlin);
                     hn[j] = (1.0f - zg) * ng + zg * h0v[e];
+                    if (saved && live) {  // planes 1..5 of saved[6][n][D]: r, z, n, W_hn h0 + b_hn, h0
+                        const size_t plane = (size_t)n_nodes_host * D, o = (size_t)row * D + c;
+                        saved[plane + o] = rg;
+                        saved[2 * plane + o] = zg;
+                        saved[3 * plane + o] = ng;
+                        saved[4 * plane + o] = hlin;
+                        saved[5 * plane + o] = h0v[e];
+                    }
                 }
             }
             if (live) {
@@ -369,7 +386,7 @@ template <int D, bool HH>
 int launch_node_tc(const float *agg, const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                    const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                    const float *W_final, int act, int64_t n_nodes, const int64_t *n_nodes_dev, float *hidden,
-                   float *as8, float *score, cudaStream_t st) {
+                   float *as8, float *score, const float *drop_mask, float *saved, cudaStream_t st) {
     constexpr size_t smem = TcSmem<D>::TOTAL;
     static_assert(smem <= 232448, "tile does not fit the 227 KB shared memory of one CTA");
     auto kern = k_node_update_tc<D, HH>;
@@ -380,7 +397,7 @@ int launch_node_tc(const float *agg, const float *h_prev, const int32_t *src, co
     const int64_t n_tiles = (n_nodes + kTcRows - 1) / kTcRows;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);  // persistent: one CTA per SM
     kern<<<grid, 128 * (D / 16), smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
-                                         n_nodes, n_nodes_dev, hidden, as8, score);
+                                         n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -393,12 +410,12 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
                       const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                       const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                       const float *W_final, int32_t act, float *hidden, float *as8, float *score,
-                      cudaStream_t st) {
+                      const float *drop_mask, float *saved, cudaStream_t st) {
 #define RG_NODE_TC(DD)                                                                                             \
     return h_prev ? launch_node_tc<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,  \
-                                             n_nodes, n_nodes_dev, hidden, as8, score, st)                         \
+                                             n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, st)       \
                   : launch_node_tc<DD, false>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act, \
-                                              n_nodes, n_nodes_dev, hidden, as8, score, st)
+                                              n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, st)
     switch (hidden_dim) {
         case 16: RG_NODE_TC(16);
         case 32: RG_NODE_TC(32);

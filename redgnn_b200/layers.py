@@ -11,7 +11,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .ops import Segments, edge_aggregate, edge_agg_forward, node_update, scatter_scores, ACT_CODES
+from .ops import (Segments, edge_aggregate, edge_agg_forward, node_update, scatter_scores, ACT_CODES,
+                  NodeUpdateTrain)
 
 SUPPORTED_DIMS = (16, 32, 48, 64)
 
@@ -45,6 +46,10 @@ class GNNLayer(torch.nn.Module):
         self.W_h = nn.Linear(in_dim, out_dim, bias=False)
 
     def propagate(self, q_rel, hidden, fwd_seg, bwd_seg):
+        """models.py:23-43: edge aggregation followed by act(W_h .)."""
+        return self.act(self.W_h(self.aggregate(q_rel, hidden, fwd_seg, bwd_seg)))
+
+    def aggregate(self, q_rel, hidden, fwd_seg, bwd_seg):
         """Shared core.  hidden may be None (== all zeros, layer 0).  The attention projections are
         per node / per relation / per query (tiny dense maps, left to torch + autograd); everything
         per edge is one fused kernel forward and one backward."""
@@ -57,8 +62,7 @@ class GNNLayer(torch.nn.Module):
             # explicit zero (not None), which Adam's weight decay still acts on -- keep that
             aq8 = aq8 + 0.0 * self.Ws_attn.weight.sum()
         w8 = _pad8(self.w_alpha.weight).reshape(8)
-        agg = edge_aggregate(hidden, as8, rela, ar8, aq8, w8, self.w_alpha.bias, fwd_seg, bwd_seg)
-        return self.act(self.W_h(agg))
+        return edge_aggregate(hidden, as8, rela, ar8, aq8, w8, self.w_alpha.bias, fwd_seg, bwd_seg)
 
     def forward(self, q_sub, q_rel, hidden, edges, n_node, old_nodes_new_idx):
         """models.py:23-43 for a caller-provided edge list
@@ -133,6 +137,7 @@ class RedGNN(torch.nn.Module):
     # cudaGraphLaunch instead of milliseconds of host time.
     use_cuda_graph = True
     inference_in_eval = True
+    fused_train_node_update = True     # autograd path: node update in the tcgen05 kernel (hidden_dim <= 48)
     MAX_CACHED_GRAPHS = 4
 
     def _run_graph(self, q_sub, q_rel, graph, n_ent_out):
@@ -256,16 +261,30 @@ class RedGNN(torch.nn.Module):
                                                   ACT_CODES[self.act_name], ws_next,
                                                   self.W_final.weight if last else None)
             else:
-                remap = fr.remap_to(fr_next, n_nodes)
                 bwd_seg = None
                 if need_grad:
                     bwd_seg = Segments.implicit(node_b, node_e, graph.out_ptr, graph.out_adj, fr_next, graph.heavy_out)
                     bwd_seg.n_edges = n_edges
-                hidden = layer.propagate(q_rel, hidden, fwd_seg, bwd_seg)
-                h0 = torch.zeros((n_next, d), device=dev).index_copy_(0, remap, h0)
-                hidden = self.dropout(hidden)
-                hidden = self._gate(hidden, h0)
-                h0 = hidden
+                if need_grad and d <= 48 and self.fused_train_node_update:
+                    # per-node work in the tcgen05 kernel (gates saved for an explicit backward)
+                    remap, src = fr.remap_both(fr_next, n_nodes, n_next)
+                    agg = layer.aggregate(q_rel, hidden, fwd_seg, bwd_seg)
+                    mask = None
+                    if self.training and self.dropout.p > 0:
+                        keep = 1.0 - self.dropout.p
+                        mask = (torch.rand((n_next, d), device=dev) < keep).to(torch.float32).div_(keep)
+                    g = self.gate
+                    hidden = NodeUpdateTrain.apply(agg, hidden, layer.W_h.weight, g.weight_ih_l0, g.weight_hh_l0,
+                                                   g.bias_ih_l0, g.bias_hh_l0, mask,
+                                                   src if hidden is not None else None,
+                                                   remap if hidden is not None else None, ACT_CODES[self.act_name])
+                else:
+                    remap = fr.remap_to(fr_next, n_nodes)
+                    hidden = layer.propagate(q_rel, hidden, fwd_seg, bwd_seg)
+                    h0 = torch.zeros((n_next, d), device=dev).index_copy_(0, remap, h0)
+                    hidden = self.dropout(hidden)
+                    hidden = self._gate(hidden, h0)
+                    h0 = hidden
             fr, node_b, node_e, n_nodes = fr_next, nb, ne, n_next
             edges_per_layer.append(n_edges)
 

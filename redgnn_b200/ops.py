@@ -161,6 +161,57 @@ def node_update(agg, h_prev, src, W_h, gate, act_code, Ws_next8=None, W_final=No
     return hidden, as8, score
 
 
+class NodeUpdateTrain(torch.autograd.Function):
+    """Training node update: hidden = GRU(dropout(act(W_h agg)), h0) with h0[j] = h_prev[src[j]].
+    Forward = the tcgen05 kernel (rg_node_update_train, also saves the gates); backward = one
+    elementwise kernel (rg_gru_bwd_elem) + six library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, agg, h_prev, W_h, w_ih, w_hh, b_ih, b_hh, mask, src, remap, act_code):
+        agg, h_prev, W_h, w_ih, w_hh, b_ih, b_hh, mask = (_f32c(t) for t in (agg, h_prev, W_h, w_ih, w_hh, b_ih,
+                                                                             b_hh, mask))
+        n, d = agg.shape
+        hidden = torch.empty((n, d), dtype=torch.float32, device=agg.device)
+        saved = torch.empty((6, n, d), dtype=torch.float32, device=agg.device)
+        with _lib.Stats.timed("node_update_train", (n, d)):
+            check(lib.rg_node_update_train(d, n, ptr(agg), ptr(h_prev), ptr(src), ptr(W_h), ptr(w_ih), ptr(w_hh),
+                                           ptr(b_ih), ptr(b_hh), act_code, ptr(mask), ptr(hidden), ptr(saved),
+                                           stream_ptr()))
+        _lib.Stats.launches += 1
+        ctx.save_for_backward(agg, saved, W_h, w_ih, w_hh, mask if mask is not None else agg.new_empty(0),
+                              remap if remap is not None else agg.new_empty(0, dtype=torch.int64))
+        ctx.act_code, ctx.has_h0, ctx.has_mask = act_code, h_prev is not None, mask is not None
+        return hidden
+
+    @staticmethod
+    def backward(ctx, g_h):
+        agg, saved, W_h, w_ih, w_hh, mask, remap = ctx.saved_tensors
+        n, d = agg.shape
+        g_h = g_h.to(torch.float32).contiguous()
+        g_gi = torch.empty((n, 3 * d), dtype=torch.float32, device=agg.device)
+        g_gh = torch.empty((n, 3 * d), dtype=torch.float32, device=agg.device)
+        g_h0d = torch.empty((n, d), dtype=torch.float32, device=agg.device)
+        check(lib.rg_gru_bwd_elem(d, n, ptr(g_h), ptr(saved), ptr(g_gi), ptr(g_gh), ptr(g_h0d), stream_ptr()))
+        _lib.Stats.launches += 1
+        x_act, h0 = saved[0], saved[5]
+        x_in = x_act * mask if ctx.has_mask else x_act
+        g_x = g_gi @ w_ih
+        d_wih, d_bih, d_bhh = g_gi.t() @ x_in, g_gi.sum(0), g_gh.sum(0)
+        if ctx.has_mask:
+            g_x = g_x * mask
+        if ctx.act_code == 1:
+            g_x = g_x * (x_act > 0)
+        elif ctx.act_code == 2:
+            g_x = g_x * (1.0 - x_act * x_act)
+        g_agg, d_wh = g_x @ W_h, g_x.t() @ agg
+        if ctx.has_h0:
+            d_whh = g_gh.t() @ h0
+            g_prev = torch.addmm(g_h0d, g_gh, w_hh).index_select(0, remap)
+        else:
+            d_whh, g_prev = torch.zeros_like(w_hh), None
+        return g_agg, g_prev, d_wh, d_wih, d_whh, d_bih, d_bhh, None, None, None, None
+
+
 class EdgeAggregate(torch.autograd.Function):
     """agg[s] = sum_{edges e into s} alpha_e * (hidden[p_e] + rela[r_e]),
     alpha_e = sigmoid(b_alpha + sum_k w8[k] relu(as8[p_e][k] + ar8[r_e][k] + aq8[q_e][k]))."""
