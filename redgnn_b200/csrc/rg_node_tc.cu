@@ -322,6 +322,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                     const float4 hl = *reinterpret_cast<const float4 *>(smem + L::H_LO + L::off(trow, c0 / 4 + q));
                     h0v[0] = hh.x + hl.x; h0v[1] = hh.y + hl.y; h0v[2] = hh.z + hl.z; h0v[3] = hh.w + hl.w;
                 }
+                float sv[5][4];  // r, z, n, W_hn h0 + b_hn, h0 of these 4 columns (training only)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = 4 * q + e, c = c0 + j;
@@ -330,14 +331,14 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                     const float hlin = (HAS_H0 ? vh[j] : 0.f) + bias[3 * D + c];
                     const float ng = tanh_tc(vi[j] + bias[2 * D + c] + rg * hlin);
                     hn[j] = (1.0f - zg) * ng + zg * h0v[e];
-                    if (saved && live) {  // planes 1..5 of saved[6][n][D]: r, z, n, W_hn h0 + b_hn, h0
-                        const size_t plane = (size_t)n_nodes_host * D, o = (size_t)row * D + c;
-                        saved[plane + o] = rg;
-                        saved[2 * plane + o] = zg;
-                        saved[3 * plane + o] = ng;
-                        saved[4 * plane + o] = hlin;
-                        saved[5 * plane + o] = h0v[e];
-                    }
+                    sv[0][e] = rg; sv[1][e] = zg; sv[2][e] = ng; sv[3][e] = hlin; sv[4][e] = h0v[e];
+                }
+                if (saved && live) {  // planes 1..5 of saved[6][n][D], 128-bit stores
+                    const size_t plane = (size_t)n_nodes_host * D, o = (size_t)row * D + c0 + 4 * q;
+#pragma unroll
+                    for (int pl = 0; pl < 5; ++pl)
+                        *reinterpret_cast<float4 *>(saved + (pl + 1) * plane + o) =
+                            make_float4(sv[pl][0], sv[pl][1], sv[pl][2], sv[pl][3]);
                 }
             }
             if (live) {
