@@ -38,6 +38,11 @@ WORKLOADS = {  # name -> (synth shape, n_layer, default per-GPU batch)
     "powerlaw": ("powerlaw", 6, 4),      # built from arrays (ArrayLoader): 10 M triples, no text round trip
 }
 ARRAY_WORKLOADS = ("powerlaw",)
+# BASELINE configs[1]: Static/inductive on an fb237_v2-shaped pair of KGs (train graph 2,608 entities /
+# 9,739 triples, unseen-entity graph 1,660 entities / 4,145 triples, 200 relations), n_layer 3
+INDUCTIVE_WORKLOADS = {"fb237v2": dict(n_ent=2608, n_ent_ind=1660, n_rel=200, n_train=9739, n_ind_train=4145,
+                                       n_eval=1170)}
+WORKLOADS["fb237v2"] = ("fb237v2", 3, 128)
 HIDDEN, ATTN = 48, 5
 
 
@@ -130,6 +135,17 @@ def run_reference(args):
         data = _D()
         data.test_graph = O.Graph(ld._test_graph.triples, ld.n_ent, ld.n_rel)
         data.test_q, data.n_rel = ld.test_q, ld.n_rel
+    elif args.workload in INDUCTIVE_WORKLOADS:
+        from redgnn_b200 import synth
+
+        class _D(object):
+            pass
+        n_layer = WORKLOADS[args.workload][1]
+        task = synth.write_inductive(os.path.join(tempfile.mkdtemp(prefix="rg_bench_"), args.workload), seed=0,
+                                     **INDUCTIVE_WORKLOADS[args.workload])
+        ind = O.InductiveData(task)
+        data = _D()
+        data.test_graph, data.test_q, data.n_rel = ind.ind_graph, ind.test_q, ind.n_rel
     else:
         task, n_layer, _ = make_dataset(args.workload)
         data = O.TransductiveData(task)
@@ -163,6 +179,11 @@ def run_reference(args):
 
 def workload_name(workload, n_layer):
     from redgnn_b200 import synth
+    if workload in INDUCTIVE_WORKLOADS:
+        w = INDUCTIVE_WORKLOADS[workload]
+        return ("%s-shaped synthetic inductive pair (train KG %d entities / %d triples, unseen-entity KG %d entities "
+                "/ %d triples, %d relations + inverses), n_layer=%d, eval forward on the unseen-entity graph" % (
+                    workload, w["n_ent"], w["n_train"], w["n_ent_ind"], w["n_ind_train"], w["n_rel"], n_layer))
     ne, nr, nt = synth.SHAPES[WORKLOADS[workload][0]][:3]
     return "%s-shaped synthetic KG (%d entities, %d relations + inverses, %d triples), n_layer=%d, eval forward" % (
         workload, ne, nr, nt, n_layer)
@@ -208,9 +229,16 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    inductive = args.workload in INDUCTIVE_WORKLOADS
     if args.workload in ARRAY_WORKLOADS:
         shape, n_layer, batch = WORKLOADS[args.workload]
         loader, task = synth.ArrayLoader(shape, seed=0, device=dev), None
+    elif inductive:
+        _, n_layer, batch = WORKLOADS[args.workload]
+        task = synth.write_inductive(os.path.join(tempfile.mkdtemp(prefix="rg_bench_"), args.workload), seed=0,
+                                     **INDUCTIVE_WORKLOADS[args.workload])
+        with contextlib.redirect_stdout(io.StringIO()):
+            loader = redgnn_b200.InductiveLoader(task, device=dev)
     else:
         task, n_layer, batch = make_dataset(args.workload)
         with contextlib.redirect_stdout(io.StringIO()):
@@ -218,14 +246,17 @@ def main():
     batch = args.batch or batch
     opts = synth.Options(hidden_dim=HIDDEN, attn_dim=ATTN, n_layer=n_layer, n_rel=loader.n_rel, dropout=0.0)
     torch.manual_seed(1234)
-    model = redgnn_b200.RED_GNN_trans(opts, loader).to(dev)
+    model = (redgnn_b200.RED_GNN_induc if inductive else redgnn_b200.RED_GNN_trans)(opts, loader).to(dev)
     optim = torch.optim.Adam(model.parameters(), lr=1e-3) if args.train else None
     model.train() if args.train else model.eval()
-    mode = "train" if args.train else "test"
+    if inductive:       # train on the training graph, evaluate on the unseen-entity graph
+        mode = "transductive" if args.train else "inductive"
+    else:
+        mode = "train" if args.train else "test"
 
     # query stream: rank r takes batches r, r+world, ... of the test queries (train triples for --train)
     if args.train:
-        pool = loader.train_data[:, :3]
+        pool = (loader.tra_train if inductive else loader.train_data)[:, :3]
     else:
         tq = np.array(loader.test_q)
         pool = np.concatenate([tq, np.zeros((len(tq), 1), dtype=tq.dtype)], 1)
@@ -243,7 +274,7 @@ def main():
     def run_step(subs, rels, objs):
         if args.train:
             optim.zero_grad(set_to_none=True)
-            scores = model(subs, rels)
+            scores = model(subs, rels, mode)
             pos = scores[torch.arange(len(scores), device=dev), objs]
             mx = scores.max(1, keepdim=True)[0]
             loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(scores - mx), 1)))
@@ -321,7 +352,8 @@ def main():
 
     # ---------------- end-to-end timing through the public API with host buffers (e2e) ----------------
     host_batches = [step_batch(1, i) for i in range(n_steps_total)]
-    pinned_out = torch.empty((batch, loader.n_ent), dtype=torch.float32).pin_memory()
+    n_ent_out = loader.n_ent_for(mode)
+    pinned_out = torch.empty((batch, n_ent_out), dtype=torch.float32).pin_memory()
     for i in range(args.warmup):
         b = host_batches[i]
         out = run_step(b[:, 0], b[:, 1], torch.as_tensor(b[:, 2]).to(dev))
@@ -377,7 +409,7 @@ def main():
                    "l2": "flushed between timed steps (256 MiB write, untimed)", "parallelism": "dp%d" % world},
         "e2e": {"value": world * batch * args.steps / t_e2e, "unit": "queries/s",
                 "h2d_bytes_per_step": int(batch * 16 + (batch * 8 if args.train else 0)),
-                "d2h_bytes_per_step": int(4 if args.train else batch * loader.n_ent * 4)},
+                "d2h_bytes_per_step": int(4 if args.train else batch * n_ent_out * 4)},
         "gpu_launches": int(launches),
         "kernel_ms_per_step": {k: round(v, 4) for k, v in kernel_ms.items()},
         "roofline": {"bound": "hbm", "kernel": "k_edge_fwd (fused gather+attention+segmented reduce)",
@@ -389,7 +421,13 @@ def main():
     }
     if not args.no_cpu_baseline:
         from oracle import redgnn_oracle as O
-        if task is None:
+        if inductive:
+            class _D(object):
+                pass
+            ind = O.InductiveData(task)
+            data = _D()
+            data.test_graph, data.test_q = ind.ind_graph, ind.test_q
+        elif task is None:
             class _D(object):
                 pass
             data = _D()
