@@ -204,12 +204,26 @@ int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_d
  * backward pass.  rg_gru_bwd_elem is the elementwise part of that backward:
  *   g_gi[n][3D], g_gh[n][3D] = gradients of the GRU pre-activations (r, z, n) on the input / hidden
  *   side, g_h0_direct[n][D] = g_hidden * z; the GEMMs around it are plain library calls. */
-int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const float *agg, const float *h_prev,
+int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev,
+                         const float *agg, const float *h_prev,
                          const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                          const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
                          float *hidden, float *saved, void *stream);
-int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const float *g_hidden, const float *saved,
-                    float *g_gi, float *g_gh, float *g_h0_direct, void *stream);
+int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *g_hidden,
+                    const float *saved, float *g_gi, float *g_gh, float *g_h0_direct, void *stream);
+
+/* Glue of the graph-captured training step (all shape-static, true counts read on the device):
+ *   rg_gather_scores: backward of rg_scatter_scores, g_node[j] = g_scores_all[b_j][e_j] (0 past n);
+ *   rg_scatter_rows : dst[src[j]] = rows[j] for src[j] >= 0 -- gradient of the h0 re-index
+ *                     (models.py:81), src = the inverse map of rg_frontier_remap;
+ *   rg_query_sum8   : out[q][0..7] = sum of rows24[.][0..7] over the node rows of query q
+ *                     (rg_frontier.qinfo ranges) -- the per-query attention-bias gradient, fixed order. */
+int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
+                     const int32_t *node_e, const float *g_scores_all, int32_t n_ent_out, float *g_node,
+                     void *stream);
+int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *src,
+                    const float *rows, float *dst, void *stream);
+int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *out, void *stream);
 
 /* scores_all[node_b[j]][node_e[j]] = score[j] for j < n (models.py:87-88; scores_all is zeroed by
  * the caller, so unvisited entities keep an exact 0). */

@@ -55,8 +55,11 @@ SIGNATURES = {
     "rg_frontier_remap": (C.c_int, [C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 4),
-    "rg_node_update_train": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 8 + [C.c_int32] + [C.c_void_p] * 4),
-    "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 6),
+    "rg_node_update_train": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 9 + [C.c_int32] + [C.c_void_p] * 4),
+    "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 7),
+    "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
+    "rg_scatter_rows": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 5),
+    "rg_query_sum8": (C.c_int, [C.c_int32] + [C.c_void_p] * 4),
     "rg_scatter_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
     "rg_edges_emit": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p,
                                 C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -251,6 +251,76 @@ __global__ void __launch_bounds__(256) k_scatter_scores(int64_t n_host, const in
     if (i < n) out[(size_t)node_b[i] * n_ent_out + node_e[i]] = score[i];
 }
 
+// backward of the score scatter: g_node[j] = g_scores_all[node_b[j]][node_e[j]] (0 past the count)
+__global__ void __launch_bounds__(256) k_gather_scores(int64_t n_host, const int64_t *__restrict__ n_dev,
+                                                       const int32_t *__restrict__ node_b,
+                                                       const int32_t *__restrict__ node_e,
+                                                       const float *__restrict__ g_all, int n_ent_out,
+                                                       float *__restrict__ g_node) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_host) return;
+    const int64_t n = n_dev ? *n_dev : n_host;
+    g_node[i] = i < n ? g_all[(size_t)node_b[i] * n_ent_out + node_e[i]] : 0.f;
+}
+
+// dst[src[j]] = rows[j] for j < n with src[j] >= 0 (src injective): gradient of the h0 re-index
+__global__ void __launch_bounds__(256) k_scatter_rows(int64_t n_host, const int64_t *__restrict__ n_dev, int D4,
+                                                      const int32_t *__restrict__ src,
+                                                      const float4 *__restrict__ rows, float4 *__restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t n = n_dev ? *n_dev : n_host;
+    const int64_t j = i / D4;
+    if (j >= n) return;
+    const int s = src[j];
+    if (s >= 0) dst[(size_t)s * D4 + (i % D4)] = rows[i];
+}
+
+// out[q][0..7] = sum over the query's node rows [base, base+count) of rows24[.][0..7]; fixed order
+__global__ void __launch_bounds__(256) k_query_sum8(const float *__restrict__ rows24, const int32_t *__restrict__ qinfo,
+                                                    float *__restrict__ out) {
+    __shared__ float sm[32][8];
+    const int q = blockIdx.x, k = threadIdx.x & 7, t = threadIdx.x >> 3;  // 32 row-threads x 8 columns
+    const int base = qinfo[2 * q], cnt = qinfo[2 * q + 1];
+    float acc = 0.f;
+    for (int r = t; r < cnt; r += 32) acc += rows24[(size_t)(base + r) * 24 + k];
+    sm[t][k] = acc;
+    __syncthreads();
+    if (t == 0) {
+        float s = 0.f;
+        for (int i = 0; i < 32; ++i) s += sm[i][k];
+        out[q * 8 + k] = s;
+    }
+}
+
+extern "C" int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
+                                const int32_t *node_e, const float *g_scores_all, int32_t n_ent_out, float *g_node,
+                                void *stream) {
+    if (n_nodes < 0 || !node_b || !node_e || !g_scores_all || !g_node || n_ent_out <= 0) return RG_ERR_BAD_ARG;
+    if (n_nodes == 0) return RG_OK;
+    k_gather_scores<<<(unsigned)rg_cdiv(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(
+        n_nodes, n_nodes_dev, node_b, node_e, g_scores_all, n_ent_out, g_node);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
+
+extern "C" int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *src,
+                               const float *rows, float *dst, void *stream) {
+    if (n_nodes < 0 || hidden_dim <= 0 || hidden_dim % 4 || !src || !rows || !dst) return RG_ERR_BAD_ARG;
+    if (n_nodes == 0) return RG_OK;
+    const int d4 = hidden_dim / 4;
+    k_scatter_rows<<<(unsigned)rg_cdiv(n_nodes * d4, 256), 256, 0, (cudaStream_t)stream>>>(
+        n_nodes, n_nodes_dev, d4, src, reinterpret_cast<const float4 *>(rows), reinterpret_cast<float4 *>(dst));
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
+
+extern "C" int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *out, void *stream) {
+    if (n_query <= 0 || !rows24 || !qinfo || !out) return RG_ERR_BAD_ARG;
+    k_query_sum8<<<n_query, 256, 0, (cudaStream_t)stream>>>(rows24, qinfo, out);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
+
 extern "C" int rg_scatter_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
                                  const int32_t *node_e, const float *score, int32_t n_ent_out,
                                  float *scores_all, void *stream) {
@@ -270,13 +340,21 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
                       const float *drop_mask, float *saved, cudaStream_t st);
 
 // elementwise part of the GRU-cell backward (the GEMMs around it are plain library calls)
-__global__ void __launch_bounds__(256) k_gru_bwd_elem(int64_t n_elem, int D, const float *__restrict__ g_h,
+__global__ void __launch_bounds__(256) k_gru_bwd_elem(int64_t n_elem, int D, const int64_t *__restrict__ n_dev,
+                                                      const float *__restrict__ g_h,
                                                       const float *__restrict__ saved, float *__restrict__ g_gi,
                                                       float *__restrict__ g_gh, float *__restrict__ g_h0d) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_elem) return;
     const int64_t node = i / D;
     const int c = (int)(i % D);
+    if (n_dev && node >= *n_dev) {  // rows past the true node count (upper-bound buffers): exact zeros
+        float *gi = g_gi + node * 3 * D, *gh = g_gh + node * 3 * D;
+        gi[c] = gi[D + c] = gi[2 * D + c] = 0.f;
+        gh[c] = gh[D + c] = gh[2 * D + c] = 0.f;
+        g_h0d[i] = 0.f;
+        return;
+    }
     const float r = saved[n_elem + i], z = saved[2 * n_elem + i], nn = saved[3 * n_elem + i];
     const float hl = saved[4 * n_elem + i], h0 = saved[5 * n_elem + i], g = g_h[i];
     const float g_np = g * (1.f - z) * (1.f - nn * nn);   // d/d(pre-activation of n)
@@ -292,20 +370,22 @@ __global__ void __launch_bounds__(256) k_gru_bwd_elem(int64_t n_elem, int D, con
     g_h0d[i] = g * z;
 }
 
-extern "C" int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const float *g_hidden, const float *saved,
-                               float *g_gi, float *g_gh, float *g_h0_direct, void *stream) {
+extern "C" int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev,
+                               const float *g_hidden, const float *saved, float *g_gi, float *g_gh,
+                               float *g_h0_direct, void *stream) {
     if (n_nodes < 0 || hidden_dim <= 0 || !g_hidden || !saved || !g_gi || !g_gh || !g_h0_direct) return RG_ERR_BAD_ARG;
     if (n_nodes == 0) return RG_OK;
     const int64_t n_elem = n_nodes * hidden_dim;
-    k_gru_bwd_elem<<<(unsigned)rg_cdiv(n_elem, 256), 256, 0, (cudaStream_t)stream>>>(n_elem, hidden_dim, g_hidden,
-                                                                                  saved, g_gi, g_gh, g_h0_direct);
+    k_gru_bwd_elem<<<(unsigned)rg_cdiv(n_elem, 256), 256, 0, (cudaStream_t)stream>>>(
+        n_elem, hidden_dim, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
 
 // training forward: tensor-core kernel only (hidden_dim <= 48); also writes saved[6][n][D] =
 // {act(W_h agg) before dropout, r, z, n, W_hn h0 + b_hn, h0} for the backward pass
-extern "C" int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const float *agg, const float *h_prev,
+extern "C" int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev,
+                                    const float *agg, const float *h_prev,
                                     const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                                     const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
                                     float *hidden, float *saved, void *stream) {
@@ -313,7 +393,7 @@ extern "C" int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const f
     if ((h_prev == nullptr) != (src == nullptr) || act < 0 || act > 2) return RG_ERR_BAD_ARG;
     if (hidden_dim > 48) return RG_ERR_UNSUPPORTED;
     if (n_nodes == 0) return RG_OK;
-    return rg_node_update_tc(hidden_dim, n_nodes, nullptr, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, nullptr,
+    return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, nullptr,
                              nullptr, act, hidden, nullptr, nullptr, drop_mask, saved, (cudaStream_t)stream);
 }
 

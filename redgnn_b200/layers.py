@@ -170,6 +170,30 @@ class RedGNN(torch.nn.Module):
         self._last_stats = entry["frontiers"]
         return entry["out"].clone()
 
+    # Training: forward and hand-written backward of the whole path captured as two CUDA graphs
+    # (train_graph.py); the eager autograd path below remains for hidden_dim 64 / profiling.
+    graph_train = True
+    MAX_CACHED_TRAIN_GRAPHS = 2
+
+    def _run_train_graph(self, q_sub, q_rel, graph, n_ent_out):
+        from .train_graph import TrainStepRunner, TrainStepFunction
+        p_drop = float(self.dropout.p) if self.training else 0.0
+        key = (q_sub.shape[0], id(graph), n_ent_out, p_drop, tuple(p.data_ptr() for p in self.parameters()))
+        cache = self.__dict__.setdefault("_train_graph_cache", {})
+        runner = cache.get(key)
+        if runner is None:
+            while len(cache) >= self.MAX_CACHED_TRAIN_GRAPHS:
+                cache.pop(next(iter(cache)))
+            saved_p, self.dropout.p = self.dropout.p, p_drop
+            try:
+                runner = TrainStepRunner(self, graph, q_sub.shape[0], n_ent_out)
+            finally:
+                self.dropout.p = saved_p
+            cache[key] = runner
+        scores = TrainStepFunction.apply(runner, q_sub, q_rel, *[runner.params[k] for k in runner.names])
+        self._last_stats = runner.frontiers
+        return scores
+
     def _run_async(self, q_sub, q_rel, graph, n_ent_out):
         """Inference without ANY host synchronisation: every per-layer buffer is sized by the upper
         bound n_query * n_ent and the kernels read the true node counts from device memory
@@ -226,6 +250,9 @@ class RedGNN(torch.nn.Module):
             if self.use_cuda_graph and _lib.Stats.timing is None:
                 return self._run_graph(q_sub, q_rel, graph, n_ent_out)
             return self._run_async(q_sub, q_rel, graph, n_ent_out)
+        if need_grad and self.graph_train and d <= 48 and n > 0 and _lib.Stats.timing is None \
+                and n * graph.n_ent * d * 4 * 9 * self.n_layer <= self.ASYNC_BUDGET_BYTES:
+            return self._run_train_graph(q_sub, q_rel, graph, n_ent_out)
 
         batch = torch.arange(n, device=dev)
         fr = graph.frontier_from_nodes(torch.stack([batch, q_sub], dim=1), n)

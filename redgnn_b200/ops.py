@@ -174,7 +174,7 @@ class NodeUpdateTrain(torch.autograd.Function):
         hidden = torch.empty((n, d), dtype=torch.float32, device=agg.device)
         saved = torch.empty((6, n, d), dtype=torch.float32, device=agg.device)
         with _lib.Stats.timed("node_update_train", (n, d)):
-            check(lib.rg_node_update_train(d, n, ptr(agg), ptr(h_prev), ptr(src), ptr(W_h), ptr(w_ih), ptr(w_hh),
+            check(lib.rg_node_update_train(d, n, None, ptr(agg), ptr(h_prev), ptr(src), ptr(W_h), ptr(w_ih), ptr(w_hh),
                                            ptr(b_ih), ptr(b_hh), act_code, ptr(mask), ptr(hidden), ptr(saved),
                                            stream_ptr()))
         _lib.Stats.launches += 1
@@ -191,7 +191,7 @@ class NodeUpdateTrain(torch.autograd.Function):
         g_gi = torch.empty((n, 3 * d), dtype=torch.float32, device=agg.device)
         g_gh = torch.empty((n, 3 * d), dtype=torch.float32, device=agg.device)
         g_h0d = torch.empty((n, d), dtype=torch.float32, device=agg.device)
-        check(lib.rg_gru_bwd_elem(d, n, ptr(g_h), ptr(saved), ptr(g_gi), ptr(g_gh), ptr(g_h0d), stream_ptr()))
+        check(lib.rg_gru_bwd_elem(d, n, None, ptr(g_h), ptr(saved), ptr(g_gi), ptr(g_gh), ptr(g_h0d), stream_ptr()))
         _lib.Stats.launches += 1
         x_act, h0 = saved[0], saved[5]
         x_in = x_act * mask if ctx.has_mask else x_act

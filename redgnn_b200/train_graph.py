@@ -1,0 +1,239 @@
+"""Graph-captured training step of RED_GNN_* (forward + backward of the whole path).
+
+The eager autograd path (layers.RedGNN._run) costs ~90 framework ops and one host read-back per
+layer; at the reference's batch sizes (n_batch 3..100, Static/transductive/train.py:46-111) the
+step is host-bound by a wide margin.  Here the forward of a (batch size, KG) pair is made
+shape-static exactly like the inference path (upper-bound buffers of n_query * n_ent rows, true
+counts read on the device), the backward is written out by hand on the same buffers (fused edge
+backward, GRU elementwise kernel + library GEMMs, small projection GEMMs), and both are captured
+once as CUDA graphs.  A single torch.autograd.Function replays them, so `loss.backward()` and the
+optimiser in the caller's loop (Static/*/base_model.py:49-70) work unchanged.
+
+Invariant that makes upper-bound buffers safe: every persistent buffer starts as zeros and only ever
+holds finite values, and every gradient row past the true node count is an exact zero
+(rg_gru_bwd_elem / rg_gather_scores write zeros there, node_small is cleared per replay), so stale
+rows only ever meet zeros in the reductions over nodes.
+"""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+from .ops import Segments, _Heavy, ACT_CODES
+
+
+def _pad_rows(w, rows=8):
+    return w if w.shape[0] == rows else F.pad(w, (0, 0, 0, rows - w.shape[0]))
+
+
+class TrainStepRunner(object):
+    """Static buffers + the two CUDA graphs for one (model, KG, batch size)."""
+
+    def __init__(self, model, graph, n, n_ent_out):
+        self.model, self.graph, self.n, self.n_ent_out = model, graph, int(n), int(n_ent_out)
+        dev = model.W_final.weight.device
+        self.dev, self.d, self.a, self.n_layer = dev, model.hidden_dim, model.attn_dim, model.n_layer
+        self.cap = self.n * graph.n_ent
+        self.act_code = ACT_CODES[model.act_name]
+        self.p_drop = float(model.dropout.p)
+        self.names = [k for k, _ in model.named_parameters()]
+        self.params = dict(model.named_parameters())
+        sizes = [self.params[k].numel() for k in self.names]
+        self.flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.grad_views, off = {}, 0
+        for k, sz in zip(self.names, sizes):
+            self.grad_views[k] = self.flat_grad[off:off + sz].view_as(self.params[k])
+            off += sz
+        self.sub = torch.zeros(self.n, dtype=torch.int64, device=dev)
+        self.rel = torch.zeros(self.n, dtype=torch.int64, device=dev)
+        self.g_out = torch.zeros((self.n, self.n_ent_out), dtype=torch.float32, device=dev)
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        # persistent, finite-by-construction buffers (see module docstring)
+        self.agg = [z(self.cap, self.d) for _ in range(self.n_layer)]
+        self.hidden = [z(self.cap, self.d) for _ in range(self.n_layer)]
+        self.saved = [z(6, self.cap, self.d) for _ in range(self.n_layer)]
+        self.L = None
+        self.scores = None
+        self.version = 0
+        self._build()
+
+    # ------------------------------------------------------------------------------------------
+    def _forward(self):
+        m, g, n, d, cap, dev = self.model, self.graph, self.n, self.d, self.cap, self.dev
+        q_sub, q_rel = self.sub, self.rel
+        batch = torch.arange(n, device=dev)
+        fr = g.frontier_from_nodes(torch.stack([batch, q_sub], dim=1), n)
+        node_b, node_e = batch.to(torch.int32), q_sub.to(torch.int32)
+        onehot = torch.zeros((n, 2 * m.n_rel + 1), dtype=torch.float32, device=dev)
+        onehot.scatter_(1, q_rel[:, None], 1.0)
+        hidden, n_in_dev, L = None, None, []
+        for i in range(self.n_layer):
+            layer = m.gnn_layers[i]
+            fr_next = g.step(fr)
+            n_dev = fr_next.counts[_lib.RG_CNT_N_OUT:_lib.RG_CNT_N_OUT + 1]
+            nb, ne = fr_next.nodes32(cap)
+            src = fr.inverse_remap_to(fr_next, cap) if hidden is not None else None
+            rela = layer.rela_embed.weight
+            Ws8, Wr8, Wqr8 = _pad_rows(layer.Ws_attn.weight), _pad_rows(layer.Wr_attn.weight), \
+                _pad_rows(layer.Wqr_attn.weight)
+            bqr8 = F.pad(layer.Wqr_attn.bias, (0, 8 - self.a))
+            w8 = F.pad(layer.w_alpha.weight.reshape(-1), (0, 8 - self.a)).contiguous()
+            ar8 = (rela @ Wr8.t()).contiguous()
+            hq = onehot @ rela                                   # rela[q_rel], as a GEMM (deterministic backward)
+            aq8 = torch.addmm(bqr8, hq, Wqr8.t()).contiguous()
+            as8 = (hidden @ Ws8.t()).contiguous() if hidden is not None else None
+            fwd_seg = Segments.implicit(nb, ne, g.in_ptr, g.in_adj, fr, g.heavy_in)
+            fwd_seg.n_seg_dev, fwd_seg.n_table_rows = n_dev, rela.shape[0]
+            bwd_seg = Segments.implicit(node_b, node_e, g.out_ptr, g.out_adj, fr_next, g.heavy_out)
+            bwd_seg.n_seg_dev = n_in_dev                         # None at layer 0: exactly n query nodes
+            heavy = _Heavy(fwd_seg.heavy_bound, d, dev)
+            check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
+                                      ptr(aq8), ptr(w8), ptr(layer.w_alpha.bias), ptr(self.agg[i]), heavy.ref(),
+                                      stream_ptr()))
+            mask = None
+            if self.p_drop > 0:
+                keep = 1.0 - self.p_drop
+                mask = (torch.rand((cap, d), device=dev) < keep).to(torch.float32).div_(keep)
+            gate = m.gate
+            check(lib.rg_node_update_train(d, cap, ptr(n_dev), ptr(self.agg[i]), ptr(hidden), ptr(src),
+                                           ptr(layer.W_h.weight), ptr(gate.weight_ih_l0), ptr(gate.weight_hh_l0),
+                                           ptr(gate.bias_ih_l0), ptr(gate.bias_hh_l0), self.act_code, ptr(mask),
+                                           ptr(self.hidden[i]), ptr(self.saved[i]), stream_ptr()))
+            L.append(dict(fr_in=fr, fr_out=fr_next, n_dev=n_dev, nb=nb, ne=ne, src=src, rela=rela, Ws8=Ws8, Wr8=Wr8,
+                          Wqr8=Wqr8, w8=w8, ar8=ar8, hq=hq, aq8=aq8, as8=as8, hidden_prev=hidden, mask=mask,
+                          bwd_seg=bwd_seg, heavy=heavy, fwd_seg=fwd_seg))
+            hidden, n_in_dev, fr, node_b, node_e = self.hidden[i], n_dev, fr_next, nb, ne
+        score_node = (hidden @ m.W_final.weight.t()).reshape(-1).contiguous()
+        scores = torch.zeros((n, self.n_ent_out), dtype=torch.float32, device=dev)
+        check(lib.rg_scatter_scores(cap, ptr(n_in_dev), ptr(node_b), ptr(node_e), ptr(score_node), self.n_ent_out,
+                                    ptr(scores), stream_ptr()))
+        self.L, self.onehot = L, onehot
+        return scores
+
+    # ------------------------------------------------------------------------------------------
+    def _backward(self):
+        m, n, d, a, cap, dev = self.model, self.n, self.d, self.a, self.cap, self.dev
+        st = stream_ptr
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        grads = {}
+        last = self.L[-1]
+        g_node = e(cap)
+        check(lib.rg_gather_scores(cap, ptr(last["n_dev"]), ptr(last["nb"]), ptr(last["ne"]), ptr(self.g_out),
+                                   self.n_ent_out, ptr(g_node), st()))
+        grads["W_final.weight"] = g_node[None, :] @ self.hidden[-1]
+        g_hidden = g_node[:, None] * m.W_final.weight
+        gate = m.gate
+        w_ih, w_hh = gate.weight_ih_l0, gate.weight_hh_l0
+        d_wih, d_whh, d_bih, d_bhh = torch.zeros_like(w_ih), torch.zeros_like(w_hh), z(3 * d), z(3 * d)
+        for i in reversed(range(self.n_layer)):
+            lay, layer = self.L[i], m.gnn_layers[i]
+            pre = "gnn_layers.%d." % i
+            saved, mask = self.saved[i], lay["mask"]
+            g_hidden = g_hidden.contiguous()
+            g_gi, g_gh, g_h0d = e(cap, 3 * d), e(cap, 3 * d), e(cap, d)
+            check(lib.rg_gru_bwd_elem(d, cap, ptr(lay["n_dev"]), ptr(g_hidden), ptr(saved), ptr(g_gi), ptr(g_gh),
+                                      ptr(g_h0d), st()))
+            x_act = saved[0]
+            x_in = x_act * mask if mask is not None else x_act
+            d_wih += g_gi.t() @ x_in
+            d_bih += g_gi.sum(0)
+            d_bhh += g_gh.sum(0)
+            g_x = g_gi @ w_ih
+            if mask is not None:
+                g_x = g_x * mask
+            if self.act_code == 1:
+                g_x = g_x * (x_act > 0)
+            elif self.act_code == 2:
+                g_x = g_x * (1.0 - x_act * x_act)
+            grads[pre + "W_h.weight"] = g_x.t() @ self.agg[i]
+            g_agg = (g_x @ layer.W_h.weight).contiguous()
+            hidden_prev, g_prev = lay["hidden_prev"], None
+            if hidden_prev is not None:
+                d_whh += g_gh.t() @ saved[5]
+                g_h0 = torch.addmm(g_h0d, g_gh, w_hh)
+                g_prev = z(cap, d)
+                check(lib.rg_scatter_rows(d, cap, ptr(lay["n_dev"]), ptr(lay["src"]), ptr(g_h0), ptr(g_prev), st()))
+            # fused edge backward on the same implicit segments (grouped by the layer's INPUT nodes)
+            bwd_seg, rela = lay["bwd_seg"], lay["rela"]
+            n_seg = bwd_seg.n_seg
+            node_small = z(n_seg, 24)
+            g_hid_e = z(n_seg, d) if hidden_prev is not None else None
+            g_rela, g_ar8 = torch.zeros_like(rela), z(rela.shape[0], 8)
+            heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
+            check(lib.rg_edge_agg_bwd(C.byref(bwd_seg.c_struct()), d, ptr(hidden_prev), ptr(lay["as8"]), ptr(rela),
+                                      ptr(lay["ar8"]), ptr(lay["aq8"]), ptr(lay["w8"]), ptr(layer.w_alpha.bias),
+                                      ptr(g_agg), ptr(g_hid_e), ptr(node_small), ptr(g_rela), ptr(g_ar8), heavy.ref(),
+                                      st()))
+            lay["heavy_bwd"] = heavy
+            g_as8 = node_small[:, :8]
+            g_w8 = node_small[:, 8:16].sum(0)
+            g_aq8 = e(n, 8)
+            check(lib.rg_query_sum8(n, ptr(node_small), ptr(lay["fr_in"].qinfo), ptr(g_aq8), st()))
+            grads[pre + "w_alpha.weight"] = g_w8[:a].reshape(1, a)
+            grads[pre + "w_alpha.bias"] = node_small[:, 16].sum().reshape(1)
+            grads[pre + "Wr_attn.weight"] = (g_ar8.t() @ rela)[:a]
+            grads[pre + "Wqr_attn.weight"] = (g_aq8.t() @ lay["hq"])[:a]
+            grads[pre + "Wqr_attn.bias"] = g_aq8.sum(0)[:a]
+            g_rela = g_rela + g_ar8 @ lay["Wr8"] + self.onehot.t() @ (g_aq8 @ lay["Wqr8"])
+            grads[pre + "rela_embed.weight"] = g_rela
+            if hidden_prev is not None:
+                grads[pre + "Ws_attn.weight"] = (g_as8.t() @ hidden_prev)[:a]
+                g_hidden = g_hid_e + g_as8 @ lay["Ws8"] + g_prev
+            else:
+                grads[pre + "Ws_attn.weight"] = torch.zeros_like(layer.Ws_attn.weight)   # explicit zero (layer 0)
+        grads["gate.weight_ih_l0"], grads["gate.weight_hh_l0"] = d_wih, d_whh
+        grads["gate.bias_ih_l0"], grads["gate.bias_hh_l0"] = d_bih, d_bhh
+        for k in self.names:
+            self.grad_views[k].copy_(grads[k])
+
+    # ------------------------------------------------------------------------------------------
+    def _build(self):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():       # eager warm-up (lazy inits, workspaces)
+            self._forward()
+            self._backward()
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.fwd_graph, self.bwd_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.no_grad():
+            with torch.cuda.graph(self.fwd_graph):
+                self.scores = self._forward()
+            with torch.cuda.graph(self.bwd_graph, pool=self.fwd_graph.pool()):
+                self._backward()
+        self.frontiers = [lay["fr_out"] for lay in self.L]
+
+
+class TrainStepFunction(torch.autograd.Function):
+    """scores = forward graph; parameter gradients = backward graph.  The parameters are inputs only
+    so that autograd routes the gradients to them; the kernels read them in place."""
+
+    @staticmethod
+    def forward(ctx, runner, q_sub, q_rel, *params):
+        runner.sub.copy_(q_sub)
+        runner.rel.copy_(q_rel)
+        runner.fwd_graph.replay()
+        runner.version += 1
+        ctx.runner, ctx.version = runner, runner.version
+        return runner.scores.clone()
+
+    @staticmethod
+    def backward(ctx, g_scores):
+        r = ctx.runner
+        if ctx.version != r.version:
+            raise _lib.RgError("redgnn_b200: a graph-captured training forward was followed by another forward of "
+                               "the same batch size before its backward; set model.graph_train = False for "
+                               "interleaved forward passes")
+        r.g_out.copy_(g_scores)
+        r.bwd_graph.replay()
+        flat = r.flat_grad.clone()
+        out, off = [], 0
+        for k in r.names:
+            p = r.params[k]
+            out.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return (None, None, None) + tuple(out)

@@ -334,3 +334,38 @@ def test_fused_train_node_update_matches_composed_path(tiny_dir, act, d):
     loss_d = cuda_loss_backward(model, tri)
     assert torch.isfinite(loss_d) and all(torch.isfinite(p.grad).all() for p in model.parameters())
     assert abs(float(loss_d.detach()) - float(res[True][0])) > 0
+
+
+@pytest.mark.parametrize("act,d,fixture", [("relu", 48, "tiny_dir"), ("tanh", 32, "tiny_dir"), ("relu", 48, "hub_dir")])
+def test_graph_captured_training_step_matches_eager(request, act, d, fixture):
+    """train_graph.py: forward + hand-written backward replayed as CUDA graphs vs the eager autograd
+    path -- loss and every parameter gradient, over several batches and across an optimiser step."""
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    L = TransductiveLoader(request.getfixturevalue(fixture))
+    model = RED_GNN_trans(Options(hidden_dim=d, attn_dim=5, n_layer=3, dropout=0.0, act=act, n_rel=L.n_rel), L).cuda()
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    nb = 6 if fixture == "hub_dir" else 12
+    for it in range(3):
+        tri = L.get_batch(np.arange(it * nb, (it + 1) * nb))
+        res = {}
+        for graph in (True, False):
+            model.graph_train = graph
+            loss = cuda_loss_backward(model, tri)
+            res[graph] = (loss.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+        assert_close(res[True][0], res[False][0], 1e-5, "loss it%d" % it)
+        floor = 1e-7 * max(float(g.abs().max()) for g in res[False][1].values())
+        for k in res[True][1]:
+            a, b = res[True][1][k], res[False][1][k]
+            err, scale = (a - b).abs().max().item(), b.abs().max().item()
+            assert err <= 2e-4 * scale or err <= floor, "it%d grad %s: err %.3e scale %.3e" % (it, k, err, scale)
+        model.graph_train = True
+        opt.step()                                           # parameters change in place; graphs follow
+    assert len(model._train_graph_cache) == 1
+    st = model.last_stats
+    assert len(st["edges"]) == 3 and st["edges"][-1] > 0
+    # dropout inside the captured graph: fresh mask per replay, finite gradients
+    model.dropout.p = 0.25
+    l1 = float(cuda_loss_backward(model, tri).detach())
+    l2 = float(cuda_loss_backward(model, tri).detach())
+    assert l1 != l2 and all(torch.isfinite(p.grad).all() for p in model.parameters())
