@@ -319,6 +319,7 @@ def test_fused_train_node_update_matches_composed_path(tiny_dir, act, d):
     L = TransductiveLoader(tiny_dir)
     model = RED_GNN_trans(Options(hidden_dim=d, attn_dim=5, n_layer=3, dropout=0.0, act=act, n_rel=L.n_rel), L).cuda()
     model.train()
+    model.graph_train = False                      # eager autograd path (the graph path has its own test)
     tri = L.get_batch(np.arange(12))
     res = {}
     for fused in (True, False):
