@@ -28,6 +28,20 @@ def _pad_rows(w, rows=8):
     return w if w.shape[0] == rows else F.pad(w, (0, 0, 0, rows - w.shape[0]))
 
 
+_SPLIT = 1024
+
+
+def _tn(a, b):
+    """a^T @ b for tall operands [M, p], [M, q] (weight gradients: the reduction runs over NODES).
+    A plain GEMM gives the library one or two output tiles and a K of 10^5..10^6; split-K as a batched
+    GEMM over 1024-row slabs + a sum keeps all SMs busy and the summation order fixed."""
+    m = a.shape[0]
+    if m % _SPLIT or m < 4 * _SPLIT:
+        return a.t() @ b
+    s = m // _SPLIT
+    return torch.bmm(a.view(s, _SPLIT, -1).transpose(1, 2), b.view(s, _SPLIT, -1)).sum(0)
+
+
 class TrainStepRunner(object):
     """Static buffers + the two CUDA graphs for one (model, KG, batch size)."""
 
@@ -35,7 +49,8 @@ class TrainStepRunner(object):
         self.model, self.graph, self.n, self.n_ent_out = model, graph, int(n), int(n_ent_out)
         dev = model.W_final.weight.device
         self.dev, self.d, self.a, self.n_layer = dev, model.hidden_dim, model.attn_dim, model.n_layer
-        self.cap = self.n * graph.n_ent
+        # rows of every per-node buffer: upper bound n_query * n_ent, padded for the split-K weight gradients
+        self.cap = -(-(self.n * graph.n_ent) // _SPLIT) * _SPLIT
         self.act_code = ACT_CODES[model.act_name]
         self.p_drop = float(model.dropout.p)
         self.names = [k for k, _ in model.named_parameters()]
@@ -123,7 +138,7 @@ class TrainStepRunner(object):
         g_node = e(cap)
         check(lib.rg_gather_scores(cap, ptr(last["n_dev"]), ptr(last["nb"]), ptr(last["ne"]), ptr(self.g_out),
                                    self.n_ent_out, ptr(g_node), st()))
-        grads["W_final.weight"] = g_node[None, :] @ self.hidden[-1]
+        grads["W_final.weight"] = _tn(g_node[:, None], self.hidden[-1])
         g_hidden = g_node[:, None] * m.W_final.weight
         gate = m.gate
         w_ih, w_hh = gate.weight_ih_l0, gate.weight_hh_l0
@@ -138,7 +153,7 @@ class TrainStepRunner(object):
                                       ptr(g_h0d), st()))
             x_act = saved[0]
             x_in = x_act * mask if mask is not None else x_act
-            d_wih += g_gi.t() @ x_in
+            d_wih += _tn(g_gi, x_in)
             d_bih += g_gi.sum(0)
             d_bhh += g_gh.sum(0)
             g_x = g_gi @ w_ih
@@ -148,11 +163,11 @@ class TrainStepRunner(object):
                 g_x = g_x * (x_act > 0)
             elif self.act_code == 2:
                 g_x = g_x * (1.0 - x_act * x_act)
-            grads[pre + "W_h.weight"] = g_x.t() @ self.agg[i]
+            grads[pre + "W_h.weight"] = _tn(g_x, self.agg[i])
             g_agg = (g_x @ layer.W_h.weight).contiguous()
             hidden_prev, g_prev = lay["hidden_prev"], None
             if hidden_prev is not None:
-                d_whh += g_gh.t() @ saved[5]
+                d_whh += _tn(g_gh, saved[5])
                 g_h0 = torch.addmm(g_h0d, g_gh, w_hh)
                 g_prev = z(cap, d)
                 check(lib.rg_scatter_rows(d, cap, ptr(lay["n_dev"]), ptr(lay["src"]), ptr(g_h0), ptr(g_prev), st()))
@@ -180,7 +195,7 @@ class TrainStepRunner(object):
             g_rela = g_rela + g_ar8 @ lay["Wr8"] + self.onehot.t() @ (g_aq8 @ lay["Wqr8"])
             grads[pre + "rela_embed.weight"] = g_rela
             if hidden_prev is not None:
-                grads[pre + "Ws_attn.weight"] = (g_as8.t() @ hidden_prev)[:a]
+                grads[pre + "Ws_attn.weight"] = _tn(g_as8.contiguous(), hidden_prev)[:a]
                 g_hidden = g_hid_e + g_as8 @ lay["Ws8"] + g_prev
             else:
                 grads[pre + "Ws_attn.weight"] = torch.zeros_like(layer.Ws_attn.weight)   # explicit zero (layer 0)
