@@ -370,3 +370,33 @@ def test_graph_captured_training_step_matches_eager(request, act, d, fixture):
     l1 = float(cuda_loss_backward(model, tri).detach())
     l2 = float(cuda_loss_backward(model, tri).detach())
     assert l1 != l2 and all(torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_training_loop_graph_path_tracks_eager_path(tiny_dir):
+    """25 Adam steps from the same initialisation (dropout 0): the graph-captured step and the eager
+    autograd step follow the same loss curve, and the loss goes down."""
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    L = TransductiveLoader(tiny_dir)
+    curves = {}
+    for graph in (True, False):
+        torch.manual_seed(5)
+        model = RED_GNN_trans(Options(hidden_dim=48, attn_dim=5, n_layer=3, dropout=0.0, act="relu", n_rel=L.n_rel),
+                              L).cuda()
+        model.train()
+        model.graph_train = graph
+        opt = torch.optim.Adam(model.parameters(), lr=5e-3, weight_decay=1e-5)
+        losses = []
+        for it in range(25):
+            tri = L.get_batch(np.arange((it % 5) * 20, (it % 5 + 1) * 20))
+            opt.zero_grad()
+            out = model(tri[:, 0], tri[:, 1])
+            pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
+            mx = out.max(1, keepdim=True)[0]
+            loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1)))
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        curves[graph] = np.array(losses)
+    assert curves[True][-5:].mean() < 0.9 * curves[True][:5].mean(), curves[True]
+    rel = np.abs(curves[True] - curves[False]) / np.abs(curves[False])
+    assert rel[:5].max() < 1e-4 and rel.max() < 2e-2, rel       # fp32 chaos grows slowly with Adam steps
