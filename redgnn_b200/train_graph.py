@@ -107,6 +107,7 @@ class TrainStepRunner(object):
             check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
                                       ptr(aq8), ptr(w8), ptr(layer.w_alpha.bias), ptr(self.agg[i]), heavy.ref(),
                                       stream_ptr()))
+            _lib.Stats.launches += (3 if heavy.struct is not None else 1) + 1      # + node update below
             mask = None
             if self.p_drop > 0:
                 keep = 1.0 - self.p_drop
@@ -124,6 +125,7 @@ class TrainStepRunner(object):
         scores = torch.zeros((n, self.n_ent_out), dtype=torch.float32, device=dev)
         check(lib.rg_scatter_scores(cap, ptr(n_in_dev), ptr(node_b), ptr(node_e), ptr(score_node), self.n_ent_out,
                                     ptr(scores), stream_ptr()))
+        _lib.Stats.launches += 1
         self.L, self.onehot = L, onehot
         return scores
 
@@ -138,6 +140,7 @@ class TrainStepRunner(object):
         g_node = e(cap)
         check(lib.rg_gather_scores(cap, ptr(last["n_dev"]), ptr(last["nb"]), ptr(last["ne"]), ptr(self.g_out),
                                    self.n_ent_out, ptr(g_node), st()))
+        _lib.Stats.launches += 1
         grads["W_final.weight"] = _tn(g_node[:, None], self.hidden[-1])
         g_hidden = g_node[:, None] * m.W_final.weight
         gate = m.gate
@@ -183,6 +186,8 @@ class TrainStepRunner(object):
                                       ptr(g_agg), ptr(g_hid_e), ptr(node_small), ptr(g_rela), ptr(g_ar8), heavy.ref(),
                                       st()))
             lay["heavy_bwd"] = heavy
+            # gru elementwise + edge backward (+ chunk / fix-up kernels) + query sum (+ row scatter)
+            _lib.Stats.launches += 2 + (3 if heavy.struct is not None else 1) + (1 if hidden_prev is not None else 0)
             g_as8 = node_small[:, :8]
             g_w8 = node_small[:, 8:16].sum(0)
             g_aq8 = e(n, 8)
@@ -215,11 +220,16 @@ class TrainStepRunner(object):
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.fwd_graph, self.bwd_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        before = _lib.Stats.launches
         with torch.no_grad():
             with torch.cuda.graph(self.fwd_graph):
                 self.scores = self._forward()
+            mid = _lib.Stats.launches
             with torch.cuda.graph(self.bwd_graph, pool=self.fwd_graph.pool()):
                 self._backward()
+        # kernels of THIS library inside each graph (added to the bookkeeping at every replay)
+        self.fwd_launches, self.bwd_launches = mid - before, _lib.Stats.launches - mid
+        _lib.Stats.launches = before
         self.frontiers = [lay["fr_out"] for lay in self.L]
 
 
@@ -232,6 +242,7 @@ class TrainStepFunction(torch.autograd.Function):
         runner.sub.copy_(q_sub)
         runner.rel.copy_(q_rel)
         runner.fwd_graph.replay()
+        _lib.Stats.launches += runner.fwd_launches
         runner.version += 1
         ctx.runner, ctx.version = runner, runner.version
         return runner.scores.clone()
@@ -245,6 +256,7 @@ class TrainStepFunction(torch.autograd.Function):
                                "interleaved forward passes")
         r.g_out.copy_(g_scores)
         r.bwd_graph.replay()
+        _lib.Stats.launches += r.bwd_launches
         flat = r.flat_grad.clone()
         out, off = [], 0
         for k in r.names:
