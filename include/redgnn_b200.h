@@ -225,6 +225,15 @@ int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_
                     const float *rows, float *dst, void *stream);
 int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *out, void *stream);
 
+/* Filtered ranking on the device: utils.cal_ranks (transductive/utils.py:7-14: rankdata 'average'
+ * full rank minus 'min' filtered rank plus one, scores shifted by their row minimum + 1e-8 in
+ * float32) for the answers of every query, without the (n, n_ent) D2H copy.  ans_ptr / flt_ptr are
+ * CSR offsets [n+1] into ans_idx / flt_idx (entity ids; answers ascending per query so that the
+ * output order equals ranks[np.nonzero(ranks)] of the reference).  ranks[ans_ptr[n]] float64. */
+int rg_filtered_ranks(int32_t n_query, int32_t n_ent, const float *scores, const int32_t *ans_ptr,
+                      const int32_t *ans_idx, const int32_t *flt_ptr, const int32_t *flt_idx,
+                      double *ranks, void *stream);
+
 /* scores_all[node_b[j]][node_e[j]] = score[j] for j < n (models.py:87-88; scores_all is zeroed by
  * the caller, so unvisited entities keep an exact 0). */
 int rg_scatter_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,

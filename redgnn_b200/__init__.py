@@ -10,6 +10,7 @@ from .layers import GNNLayer, RedGNN
 from .data import TransductiveLoader, InductiveLoader
 from .transductive.models import RED_GNN_trans
 from .inductive.models import RED_GNN_induc
+from . import metrics, dist
 
 __all__ = ["DeviceGraph", "Frontier", "Segments", "edge_aggregate", "GNNLayer", "RedGNN", "TransductiveLoader",
            "InductiveLoader", "RED_GNN_trans", "RED_GNN_induc"]

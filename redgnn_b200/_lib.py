@@ -60,6 +60,7 @@ SIGNATURES = {
     "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
     "rg_scatter_rows": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 5),
     "rg_query_sum8": (C.c_int, [C.c_int32] + [C.c_void_p] * 4),
+    "rg_filtered_ranks": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 7),
     "rg_scatter_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
     "rg_edges_emit": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p,
                                 C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p]),

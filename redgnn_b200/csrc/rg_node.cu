@@ -428,3 +428,88 @@ extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t
     }
 #undef RG_NODE
 }
+
+// ------------------------------------------------------------------------------------------------
+// Filtered ranking on the device: utils.cal_ranks (reference Static/transductive/utils.py:7-14)
+// without the (n, n_ent) D2H copy and scipy.stats.rankdata.  For query row s and answer t:
+//   s'        = (s - min(s)) + 1e-8f                                   (float32, like numpy)
+//   full      = #{e : s'[e] > s'[t]} + (#{e : s'[e] == s'[t]} + 1) / 2  rankdata(-s', 'average')
+//   filtered  = 1 + #{e in filt : fs[e] > fs[t]},  fs = s' on the filter set, 0 elsewhere  ('min')
+//   rank      = full - filtered + 1
+// One CTA per query; answers of a query are processed in order (ascending entity id).
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int kRankThreads = 256;
+
+__device__ __forceinline__ float block_min(float v, float *sm) {
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = sm[0];
+    for (int i = 1; i < kRankThreads / 32; ++i) r = fminf(r, sm[i]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ int block_sum_int(int v, int *sm) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+    for (int i = 0; i < kRankThreads / 32; ++i) r += sm[i];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kRankThreads) k_filtered_ranks(const float *__restrict__ scores, int n_ent,
+                                                                 const int32_t *__restrict__ ans_ptr,
+                                                                 const int32_t *__restrict__ ans_idx,
+                                                                 const int32_t *__restrict__ flt_ptr,
+                                                                 const int32_t *__restrict__ flt_idx,
+                                                                 double *__restrict__ ranks) {
+    __shared__ float smf[kRankThreads / 32];
+    __shared__ int smi[kRankThreads / 32];
+    const int q = blockIdx.x;
+    const float *s = scores + (size_t)q * n_ent;
+    float mn = INFINITY;
+    for (int e = threadIdx.x; e < n_ent; e += kRankThreads) mn = fminf(mn, s[e]);
+    mn = block_min(mn, smf);
+    const int f0 = flt_ptr[q], f1 = flt_ptr[q + 1];
+    for (int a = ans_ptr[q]; a < ans_ptr[q + 1]; ++a) {
+        const int t = ans_idx[a];
+        const float st = (s[t] - mn) + 1e-8f;
+        int greater = 0, equal = 0, fgreater = 0, t_in_filter = 0;
+        for (int e = threadIdx.x; e < n_ent; e += kRankThreads) {
+            const float v = (s[e] - mn) + 1e-8f;
+            greater += v > st;
+            equal += v == st;
+        }
+        for (int i = f0 + threadIdx.x; i < f1; i += kRankThreads) {
+            const int e = flt_idx[i];
+            t_in_filter |= (e == t);
+            fgreater += ((s[e] - mn) + 1e-8f) > st;
+        }
+        greater = block_sum_int(greater, smi);
+        equal = block_sum_int(equal, smi);
+        fgreater = block_sum_int(fgreater, smi);
+        t_in_filter = block_sum_int(t_in_filter, smi);
+        if (threadIdx.x == 0) {
+            // answer outside its own filter set: fs[t] = 0 and every filter entry (> 0) outranks it
+            const int fcount = t_in_filter ? fgreater : (f1 - f0);
+            const double full = (double)greater + ((double)equal + 1.0) * 0.5;
+            ranks[a] = full - (1.0 + (double)fcount) + 1.0;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int rg_filtered_ranks(int32_t n_query, int32_t n_ent, const float *scores, const int32_t *ans_ptr,
+                                 const int32_t *ans_idx, const int32_t *flt_ptr, const int32_t *flt_idx,
+                                 double *ranks, void *stream) {
+    if (n_query < 0 || n_ent <= 0 || !scores || !ans_ptr || !ans_idx || !flt_ptr || !flt_idx || !ranks)
+        return RG_ERR_BAD_ARG;
+    if (n_query == 0) return RG_OK;
+    k_filtered_ranks<<<n_query, kRankThreads, 0, (cudaStream_t)stream>>>(scores, n_ent, ans_ptr, ans_idx, flt_ptr,
+                                                                       flt_idx, ranks);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
