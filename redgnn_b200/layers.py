@@ -234,6 +234,13 @@ class RedGNN(torch.nn.Module):
         dev = self.W_final.weight.device
         if dev.type != 'cuda':
             raise _lib.RgError("redgnn_b200: the model must live on a CUDA device (call .cuda()); no CPU path exists")
+        if len(subs) == 0:
+            return torch.zeros((0, n_ent_out), device=dev)
+        # the library launches on the CURRENT device / stream: make the model's device current
+        with torch.cuda.device(dev):
+            return self._run_on_device(subs, rels, graph, n_ent_out, dev)
+
+    def _run_on_device(self, subs, rels, graph, n_ent_out, dev):
         n = len(subs)
         d = self.hidden_dim
         if not isinstance(subs, torch.Tensor):

@@ -400,3 +400,27 @@ def test_training_loop_graph_path_tracks_eager_path(tiny_dir):
     assert curves[True][-5:].mean() < 0.9 * curves[True][:5].mean(), curves[True]
     rel = np.abs(curves[True] - curves[False]) / np.abs(curves[False])
     assert rel[:5].max() < 1e-4 and rel.max() < 2e-2, rel       # fp32 chaos grows slowly with Adam steps
+
+
+def test_edge_case_batches(tiny_dir):
+    """Empty batch, a single query, a batch with repeated queries, and an out-of-range subject."""
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans, _lib
+    L, D = TransductiveLoader(tiny_dir), O.TransductiveData(tiny_dir)
+    sd = O.init_state_dict(3, 48, 5, D.n_rel, seed=2)
+    model = RED_GNN_trans(Options(n_rel=L.n_rel), L).cuda()
+    model.load_state_dict(sd)
+    model.eval()
+    assert model(np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64), mode="test").shape == (0, L.n_ent)
+    subs, rels, _ = L.get_batch(np.arange(5), data="test")
+    one = model(subs[:1], rels[:1], mode="test")
+    assert_close(one, O.model_forward(sd, D.test_graph, subs[:1], rels[:1], 3, "relu"), 1e-4, "single query")
+    rep_s, rep_r = np.repeat(subs[:2], 3), np.repeat(rels[:2], 3)
+    rep = model(rep_s, rep_r, mode="test")
+    assert torch.equal(rep[0], rep[1]) and torch.equal(rep[3], rep[5])
+    assert_close(rep, O.model_forward(sd, D.test_graph, rep_s, rep_r, 3, "relu"), 1e-4, "repeated queries")
+    with pytest.raises(_lib.RgError):
+        model(np.array([L.n_ent]), np.array([0]), mode="test")
+    model.train()                                   # same edge cases through the graph-captured training path
+    out = model(subs[:1], rels[:1])
+    out.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
