@@ -210,20 +210,23 @@ int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_n
                          const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
                          float *hidden, float *saved, void *stream);
 int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *g_hidden,
-                    const float *saved, float *g_gi, float *g_gh, float *g_h0_direct, void *stream);
+                    const float *saved, float *g_gi, float *g_gh, float *g_h0_direct,
+                    float *bias_partial /* optional [ceil(n/64)][4][D]: per-CTA column sums of g_r, g_z, g_n, g_n*r */,
+                    void *stream);
 
 /* Glue of the graph-captured training step (all shape-static, true counts read on the device):
  *   rg_gather_scores: backward of rg_scatter_scores, g_node[j] = g_scores_all[b_j][e_j] (0 past n);
  *   rg_scatter_rows : dst[src[j]] = rows[j] for src[j] >= 0 -- gradient of the h0 re-index
  *                     (models.py:81), src = the inverse map of rg_frontier_remap;
- *   rg_query_sum8   : out[q][0..7] = sum of rows24[.][0..7] over the node rows of query q
- *                     (rg_frontier.qinfo ranges) -- the per-query attention-bias gradient, fixed order. */
+ *   rg_query_sum8   : partial[q][32][0..7] = slice sums of rows24[.][0..7] over the node rows of query q
+ *                     (rg_frontier.qinfo ranges); adding the 32 slices gives the per-query
+ *                     attention-bias gradient in a fixed order. */
 int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
                      const int32_t *node_e, const float *g_scores_all, int32_t n_ent_out, float *g_node,
                      void *stream);
 int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *src,
                     const float *rows, float *dst, void *stream);
-int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *out, void *stream);
+int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *partial, void *stream);
 
 /* Filtered ranking on the device: utils.cal_ranks (transductive/utils.py:7-14: rankdata 'average'
  * full rank minus 'min' filtered rank plus one, scores shifted by their row minimum + 1e-8 in

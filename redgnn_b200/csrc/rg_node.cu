@@ -275,20 +275,24 @@ __global__ void __launch_bounds__(256) k_scatter_rows(int64_t n_host, const int6
     if (s >= 0) dst[(size_t)s * D4 + (i % D4)] = rows[i];
 }
 
-// out[q][0..7] = sum over the query's node rows [base, base+count) of rows24[.][0..7]; fixed order
+// partial[q][slice][0..7] = sum over the slice's share of the query's node rows [base, base+count)
+// of rows24[.][0..7]; the caller adds the kQuerySlices partials (fixed order => deterministic)
+constexpr int kQuerySlices = 32;
 __global__ void __launch_bounds__(256) k_query_sum8(const float *__restrict__ rows24, const int32_t *__restrict__ qinfo,
-                                                    float *__restrict__ out) {
+                                                    float *__restrict__ partial) {
     __shared__ float sm[32][8];
-    const int q = blockIdx.x, k = threadIdx.x & 7, t = threadIdx.x >> 3;  // 32 row-threads x 8 columns
+    const int q = blockIdx.x, sl = blockIdx.y, k = threadIdx.x & 7, t = threadIdx.x >> 3;  // 32 row-threads x 8 cols
     const int base = qinfo[2 * q], cnt = qinfo[2 * q + 1];
+    const int per = (cnt + kQuerySlices - 1) / kQuerySlices;
+    const int lo = sl * per, hi = min(cnt, lo + per);
     float acc = 0.f;
-    for (int r = t; r < cnt; r += 32) acc += rows24[(size_t)(base + r) * 24 + k];
+    for (int r = lo + t; r < hi; r += 32) acc += rows24[(size_t)(base + r) * 24 + k];
     sm[t][k] = acc;
     __syncthreads();
     if (t == 0) {
         float s = 0.f;
         for (int i = 0; i < 32; ++i) s += sm[i][k];
-        out[q * 8 + k] = s;
+        partial[((size_t)q * kQuerySlices + sl) * 8 + k] = s;
     }
 }
 
@@ -314,9 +318,10 @@ extern "C" int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_
     return RG_OK;
 }
 
-extern "C" int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *out, void *stream) {
-    if (n_query <= 0 || !rows24 || !qinfo || !out) return RG_ERR_BAD_ARG;
-    k_query_sum8<<<n_query, 256, 0, (cudaStream_t)stream>>>(rows24, qinfo, out);
+extern "C" int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *partial,
+                             void *stream) {
+    if (n_query <= 0 || !rows24 || !qinfo || !partial) return RG_ERR_BAD_ARG;
+    k_query_sum8<<<dim3(n_query, kQuerySlices), 256, 0, (cudaStream_t)stream>>>(rows24, qinfo, partial);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -339,45 +344,80 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
                       const float *W_final, int32_t act, float *hidden, float *as8, float *score,
                       const float *drop_mask, float *saved, cudaStream_t st);
 
-// elementwise part of the GRU-cell backward (the GEMMs around it are plain library calls)
-__global__ void __launch_bounds__(256) k_gru_bwd_elem(int64_t n_elem, int D, const int64_t *__restrict__ n_dev,
-                                                      const float *__restrict__ g_h,
-                                                      const float *__restrict__ saved, float *__restrict__ g_gi,
-                                                      float *__restrict__ g_gh, float *__restrict__ g_h0d) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n_elem) return;
-    const int64_t node = i / D;
-    const int c = (int)(i % D);
-    if (n_dev && node >= *n_dev) {  // rows past the true node count (upper-bound buffers): exact zeros
+// elementwise part of the GRU-cell backward (the GEMMs around it are plain library calls).
+// One CTA = kGruRows consecutive nodes x all D columns (thread = (row lane, column)); besides the
+// per-element gradients it writes the CTA's column sums of {g_r, g_z, g_n, g_n * r} to
+// bias_partial[blockIdx][4][D] (optional) -- the bias gradients are then a tiny fixed-order sum over
+// CTAs instead of two full-matrix reductions.
+constexpr int kGruRows = 64;
+
+template <int D>
+__global__ void __launch_bounds__(4 * D) k_gru_bwd_elem(int64_t n_rows, const int64_t *__restrict__ n_dev,
+                                                        const float *__restrict__ g_h,
+                                                        const float *__restrict__ saved, float *__restrict__ g_gi,
+                                                        float *__restrict__ g_gh, float *__restrict__ g_h0d,
+                                                        float *__restrict__ bias_partial) {
+    __shared__ float sm[4][4][D];
+    const int c = threadIdx.x % D, rl = threadIdx.x / D;  // 4 row lanes
+    const int64_t n_true = n_dev ? *n_dev : n_rows, n_elem = n_rows * D;
+    const int64_t row0 = (int64_t)blockIdx.x * kGruRows;
+    float s_r = 0.f, s_z = 0.f, s_n = 0.f, s_nr = 0.f;
+    for (int k = rl; k < kGruRows; k += 4) {
+        const int64_t node = row0 + k;
+        if (node >= n_rows) break;
+        const int64_t i = node * D + c;
         float *gi = g_gi + node * 3 * D, *gh = g_gh + node * 3 * D;
-        gi[c] = gi[D + c] = gi[2 * D + c] = 0.f;
-        gh[c] = gh[D + c] = gh[2 * D + c] = 0.f;
-        g_h0d[i] = 0.f;
-        return;
+        if (node >= n_true) {  // rows past the true node count (upper-bound buffers): exact zeros
+            gi[c] = gi[D + c] = gi[2 * D + c] = 0.f;
+            gh[c] = gh[D + c] = gh[2 * D + c] = 0.f;
+            g_h0d[i] = 0.f;
+            continue;
+        }
+        const float r = saved[n_elem + i], z = saved[2 * n_elem + i], nn = saved[3 * n_elem + i];
+        const float hl = saved[4 * n_elem + i], h0 = saved[5 * n_elem + i], g = g_h[i];
+        const float g_np = g * (1.f - z) * (1.f - nn * nn);  // d/d(pre-activation of n)
+        const float g_zp = g * (h0 - nn) * z * (1.f - z);
+        const float g_rp = g_np * hl * r * (1.f - r);
+        gi[c] = g_rp;
+        gi[D + c] = g_zp;
+        gi[2 * D + c] = g_np;
+        gh[c] = g_rp;
+        gh[D + c] = g_zp;
+        gh[2 * D + c] = g_np * r;
+        g_h0d[i] = g * z;
+        s_r += g_rp;
+        s_z += g_zp;
+        s_n += g_np;
+        s_nr += g_np * r;
     }
-    const float r = saved[n_elem + i], z = saved[2 * n_elem + i], nn = saved[3 * n_elem + i];
-    const float hl = saved[4 * n_elem + i], h0 = saved[5 * n_elem + i], g = g_h[i];
-    const float g_np = g * (1.f - z) * (1.f - nn * nn);   // d/d(pre-activation of n)
-    const float g_zp = g * (h0 - nn) * z * (1.f - z);
-    const float g_rp = g_np * hl * r * (1.f - r);
-    float *gi = g_gi + node * 3 * D, *gh = g_gh + node * 3 * D;
-    gi[c] = g_rp;
-    gi[D + c] = g_zp;
-    gi[2 * D + c] = g_np;
-    gh[c] = g_rp;
-    gh[D + c] = g_zp;
-    gh[2 * D + c] = g_np * r;
-    g_h0d[i] = g * z;
+    if (bias_partial) {
+        sm[rl][0][c] = s_r;
+        sm[rl][1][c] = s_z;
+        sm[rl][2][c] = s_n;
+        sm[rl][3][c] = s_nr;
+        __syncthreads();
+        if (rl == 0) {
+            float *o = bias_partial + (size_t)blockIdx.x * 4 * D;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q * D + c] = (sm[0][q][c] + sm[1][q][c]) + (sm[2][q][c] + sm[3][q][c]);
+        }
+    }
 }
 
 extern "C" int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev,
                                const float *g_hidden, const float *saved, float *g_gi, float *g_gh,
-                               float *g_h0_direct, void *stream) {
+                               float *g_h0_direct, float *bias_partial, void *stream) {
     if (n_nodes < 0 || hidden_dim <= 0 || !g_hidden || !saved || !g_gi || !g_gh || !g_h0_direct) return RG_ERR_BAD_ARG;
     if (n_nodes == 0) return RG_OK;
-    const int64_t n_elem = n_nodes * hidden_dim;
-    k_gru_bwd_elem<<<(unsigned)rg_cdiv(n_elem, 256), 256, 0, (cudaStream_t)stream>>>(
-        n_elem, hidden_dim, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct);
+    const unsigned grid = (unsigned)rg_cdiv(n_nodes, kGruRows);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (hidden_dim) {
+        case 16: k_gru_bwd_elem<16><<<grid, 64, 0, st>>>(n_nodes, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
+        case 32: k_gru_bwd_elem<32><<<grid, 128, 0, st>>>(n_nodes, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
+        case 48: k_gru_bwd_elem<48><<<grid, 192, 0, st>>>(n_nodes, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
+        case 64: k_gru_bwd_elem<64><<<grid, 256, 0, st>>>(n_nodes, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
+        default: return RG_ERR_UNSUPPORTED;
+    }
     RG_LAUNCH_CHECK();
     return RG_OK;
 }

@@ -152,13 +152,15 @@ class TrainStepRunner(object):
             saved, mask = self.saved[i], lay["mask"]
             g_hidden = g_hidden.contiguous()
             g_gi, g_gh, g_h0d = e(cap, 3 * d), e(cap, 3 * d), e(cap, d)
+            bias_part = z(-(-cap // 64), 4, d)               # per-CTA column sums of g_r, g_z, g_n, g_n * r
             check(lib.rg_gru_bwd_elem(d, cap, ptr(lay["n_dev"]), ptr(g_hidden), ptr(saved), ptr(g_gi), ptr(g_gh),
-                                      ptr(g_h0d), st()))
+                                      ptr(g_h0d), ptr(bias_part), st()))
+            bsum = bias_part.sum(0)                          # [4, d]
             x_act = saved[0]
             x_in = x_act * mask if mask is not None else x_act
             d_wih += _tn(g_gi, x_in)
-            d_bih += g_gi.sum(0)
-            d_bhh += g_gh.sum(0)
+            d_bih += bsum[:3].reshape(-1)
+            d_bhh += torch.cat([bsum[0], bsum[1], bsum[3]])
             g_x = g_gi @ w_ih
             if mask is not None:
                 g_x = g_x * mask
@@ -190,8 +192,9 @@ class TrainStepRunner(object):
             _lib.Stats.launches += 2 + (3 if heavy.struct is not None else 1) + (1 if hidden_prev is not None else 0)
             g_as8 = node_small[:, :8]
             g_w8 = node_small[:, 8:16].sum(0)
-            g_aq8 = e(n, 8)
-            check(lib.rg_query_sum8(n, ptr(node_small), ptr(lay["fr_in"].qinfo), ptr(g_aq8), st()))
+            aq_part = e(n, 32, 8)
+            check(lib.rg_query_sum8(n, ptr(node_small), ptr(lay["fr_in"].qinfo), ptr(aq_part), st()))
+            g_aq8 = aq_part.sum(1)
             grads[pre + "w_alpha.weight"] = g_w8[:a].reshape(1, a)
             grads[pre + "w_alpha.bias"] = node_small[:, 16].sum().reshape(1)
             grads[pre + "Wr_attn.weight"] = (g_ar8.t() @ rela)[:a]
