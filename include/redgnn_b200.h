@@ -216,16 +216,16 @@ int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_
 
 /* Glue of the graph-captured training step (all shape-static, true counts read on the device):
  *   rg_gather_scores: backward of rg_scatter_scores, g_node[j] = g_scores_all[b_j][e_j] (0 past n);
- *   rg_scatter_rows : dst[src[j]] = rows[j] for src[j] >= 0 -- gradient of the h0 re-index
+ *   rg_scatter_rows : dst[src[j]] (+)= rows[j] for src[j] >= 0 -- gradient of the h0 re-index
  *                     (models.py:81), src = the inverse map of rg_frontier_remap;
- *   rg_query_sum8   : partial[q][32][0..7] = slice sums of rows24[.][0..7] over the node rows of query q
- *                     (rg_frontier.qinfo ranges); adding the 32 slices gives the per-query
- *                     attention-bias gradient in a fixed order. */
+ *   rg_query_sum8   : partial[q][32][0..23] = slice sums of rows24[.][0..23] over the node rows of query q
+ *                     (rg_frontier.qinfo ranges); adding the 32 slices gives, in a fixed order, the
+ *                     per-query attention-bias gradient (cols 0..7) and the w_alpha / b_alpha sums. */
 int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
                      const int32_t *node_e, const float *g_scores_all, int32_t n_ent_out, float *g_node,
                      void *stream);
 int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *src,
-                    const float *rows, float *dst, void *stream);
+                    const float *rows, float *dst, int32_t accumulate, void *stream);
 int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *partial, void *stream);
 
 /* Filtered ranking on the device: utils.cal_ranks (transductive/utils.py:7-14: rankdata 'average'

@@ -266,33 +266,42 @@ __global__ void __launch_bounds__(256) k_gather_scores(int64_t n_host, const int
 // dst[src[j]] = rows[j] for j < n with src[j] >= 0 (src injective): gradient of the h0 re-index
 __global__ void __launch_bounds__(256) k_scatter_rows(int64_t n_host, const int64_t *__restrict__ n_dev, int D4,
                                                       const int32_t *__restrict__ src,
-                                                      const float4 *__restrict__ rows, float4 *__restrict__ dst) {
+                                                      const float4 *__restrict__ rows, float4 *__restrict__ dst,
+                                                      int accumulate) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     const int64_t n = n_dev ? *n_dev : n_host;
     const int64_t j = i / D4;
     if (j >= n) return;
     const int s = src[j];
-    if (s >= 0) dst[(size_t)s * D4 + (i % D4)] = rows[i];
+    if (s < 0) return;
+    float4 *o = dst + (size_t)s * D4 + (i % D4);
+    float4 v = rows[i];
+    if (accumulate) {  // src is injective: no two threads touch the same destination
+        const float4 c = *o;
+        v = make_float4(v.x + c.x, v.y + c.y, v.z + c.z, v.w + c.w);
+    }
+    *o = v;
 }
 
-// partial[q][slice][0..7] = sum over the slice's share of the query's node rows [base, base+count)
-// of rows24[.][0..7]; the caller adds the kQuerySlices partials (fixed order => deterministic)
+// partial[q][slice][0..23] = sum over the slice's share of the query's node rows [base, base+count)
+// of rows24[.][0..23]; the caller adds the kQuerySlices partials (fixed order => deterministic)
 constexpr int kQuerySlices = 32;
-__global__ void __launch_bounds__(256) k_query_sum8(const float *__restrict__ rows24, const int32_t *__restrict__ qinfo,
-                                                    float *__restrict__ partial) {
-    __shared__ float sm[32][8];
-    const int q = blockIdx.x, sl = blockIdx.y, k = threadIdx.x & 7, t = threadIdx.x >> 3;  // 32 row-threads x 8 cols
+__global__ void __launch_bounds__(240) k_query_sum24(const float *__restrict__ rows24,
+                                                     const int32_t *__restrict__ qinfo,
+                                                     float *__restrict__ partial) {
+    __shared__ float sm[10][24];
+    const int q = blockIdx.x, sl = blockIdx.y, k = threadIdx.x % 24, t = threadIdx.x / 24;  // 10 row-threads x 24 cols
     const int base = qinfo[2 * q], cnt = qinfo[2 * q + 1];
     const int per = (cnt + kQuerySlices - 1) / kQuerySlices;
     const int lo = sl * per, hi = min(cnt, lo + per);
     float acc = 0.f;
-    for (int r = lo + t; r < hi; r += 32) acc += rows24[(size_t)(base + r) * 24 + k];
+    for (int r = lo + t; r < hi; r += 10) acc += rows24[(size_t)(base + r) * 24 + k];
     sm[t][k] = acc;
     __syncthreads();
     if (t == 0) {
         float s = 0.f;
-        for (int i = 0; i < 32; ++i) s += sm[i][k];
-        partial[((size_t)q * kQuerySlices + sl) * 8 + k] = s;
+        for (int i = 0; i < 10; ++i) s += sm[i][k];
+        partial[((size_t)q * kQuerySlices + sl) * 24 + k] = s;
     }
 }
 
@@ -308,12 +317,13 @@ extern "C" int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, con
 }
 
 extern "C" int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *src,
-                               const float *rows, float *dst, void *stream) {
+                               const float *rows, float *dst, int32_t accumulate, void *stream) {
     if (n_nodes < 0 || hidden_dim <= 0 || hidden_dim % 4 || !src || !rows || !dst) return RG_ERR_BAD_ARG;
     if (n_nodes == 0) return RG_OK;
     const int d4 = hidden_dim / 4;
     k_scatter_rows<<<(unsigned)rg_cdiv(n_nodes * d4, 256), 256, 0, (cudaStream_t)stream>>>(
-        n_nodes, n_nodes_dev, d4, src, reinterpret_cast<const float4 *>(rows), reinterpret_cast<float4 *>(dst));
+        n_nodes, n_nodes_dev, d4, src, reinterpret_cast<const float4 *>(rows), reinterpret_cast<float4 *>(dst),
+        accumulate);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -321,7 +331,7 @@ extern "C" int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_
 extern "C" int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *partial,
                              void *stream) {
     if (n_query <= 0 || !rows24 || !qinfo || !partial) return RG_ERR_BAD_ARG;
-    k_query_sum8<<<dim3(n_query, kQuerySlices), 256, 0, (cudaStream_t)stream>>>(rows24, qinfo, partial);
+    k_query_sum24<<<dim3(n_query, kQuerySlices), 240, 0, (cudaStream_t)stream>>>(rows24, qinfo, partial);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }

@@ -170,12 +170,10 @@ class TrainStepRunner(object):
                 g_x = g_x * (1.0 - x_act * x_act)
             grads[pre + "W_h.weight"] = _tn(g_x, self.agg[i])
             g_agg = (g_x @ layer.W_h.weight).contiguous()
-            hidden_prev, g_prev = lay["hidden_prev"], None
+            hidden_prev, g_h0 = lay["hidden_prev"], None
             if hidden_prev is not None:
                 d_whh += _tn(g_gh, saved[5])
                 g_h0 = torch.addmm(g_h0d, g_gh, w_hh)
-                g_prev = z(cap, d)
-                check(lib.rg_scatter_rows(d, cap, ptr(lay["n_dev"]), ptr(lay["src"]), ptr(g_h0), ptr(g_prev), st()))
             # fused edge backward on the same implicit segments (grouped by the layer's INPUT nodes)
             bwd_seg, rela = lay["bwd_seg"], lay["rela"]
             n_seg = bwd_seg.n_seg
@@ -189,14 +187,15 @@ class TrainStepRunner(object):
                                       st()))
             lay["heavy_bwd"] = heavy
             # gru elementwise + edge backward (+ chunk / fix-up kernels) + query sum (+ row scatter)
-            _lib.Stats.launches += 2 + (3 if heavy.struct is not None else 1) + (1 if hidden_prev is not None else 0)
+            _lib.Stats.launches += 2 + (3 if heavy.struct is not None else 1)
             g_as8 = node_small[:, :8]
-            g_w8 = node_small[:, 8:16].sum(0)
-            aq_part = e(n, 32, 8)
-            check(lib.rg_query_sum8(n, ptr(node_small), ptr(lay["fr_in"].qinfo), ptr(aq_part), st()))
-            g_aq8 = aq_part.sum(1)
-            grads[pre + "w_alpha.weight"] = g_w8[:a].reshape(1, a)
-            grads[pre + "w_alpha.bias"] = node_small[:, 16].sum().reshape(1)
+            q_part = e(n, 32, 24)
+            check(lib.rg_query_sum8(n, ptr(node_small), ptr(lay["fr_in"].qinfo), ptr(q_part), st()))
+            q_sum = q_part.sum(1)                            # [n, 24] per-query sums of node_small
+            g_aq8 = q_sum[:, :8].contiguous()
+            tot = q_sum.sum(0)
+            grads[pre + "w_alpha.weight"] = tot[8:8 + a].reshape(1, a)
+            grads[pre + "w_alpha.bias"] = tot[16:17]
             grads[pre + "Wr_attn.weight"] = (g_ar8.t() @ rela)[:a]
             grads[pre + "Wqr_attn.weight"] = (g_aq8.t() @ lay["hq"])[:a]
             grads[pre + "Wqr_attn.bias"] = g_aq8.sum(0)[:a]
@@ -204,7 +203,10 @@ class TrainStepRunner(object):
             grads[pre + "rela_embed.weight"] = g_rela
             if hidden_prev is not None:
                 grads[pre + "Ws_attn.weight"] = _tn(g_as8.contiguous(), hidden_prev)[:a]
-                g_hidden = g_hid_e + g_as8 @ lay["Ws8"] + g_prev
+                # g_hidden(prev) = edge part + attention-projection part + GRU state part (scattered in place)
+                check(lib.rg_scatter_rows(d, cap, ptr(lay["n_dev"]), ptr(lay["src"]), ptr(g_h0), ptr(g_hid_e), 1, st()))
+                _lib.Stats.launches += 1
+                g_hidden = torch.addmm(g_hid_e, g_as8, lay["Ws8"])
             else:
                 grads[pre + "Ws_attn.weight"] = torch.zeros_like(layer.Ws_attn.weight)   # explicit zero (layer 0)
         grads["gate.weight_ih_l0"], grads["gate.weight_hh_l0"] = d_wih, d_whh
