@@ -102,9 +102,6 @@ typedef struct rg_segments {
     const int32_t *peer_qinfo;     /* implicit, optional: rg_frontier.qinfo of the peer frontier     */
     int32_t n_table_rows;          /* rows of the relation tables (2R+1); > 0 lets the forward kernel
                                       stage rela / ar8 in shared memory when they fit            */
-    int32_t hidden_ld;             /* forward only: 0 = hidden rows of D floats + separate as8[.][8];
-                                      > 0 = PACKED rows of hidden_ld floats [D hidden | 8 as8 | pad]
-                                      (as8 argument NULL); 64 at D = 48 selects the 8-lane kernel   */
 } rg_segments;
 
 /* Queue for segments longer than RG_HEAVY_CHUNK candidate slots: they are cut into chunks that
@@ -196,15 +193,10 @@ int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
  * h_prev and src are both NULL at layer 0 (h0 == 0).  act: 0 identity, 1 relu, 2 tanh.
  * n_nodes is an upper bound when n_nodes_dev (device-resident true count) is given. */
 int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
-                   const float *h_prev /* rows of prev_ld floats */,
+                   const float *h_prev,
                    const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                    const float *b_ih, const float *b_hh, const float *Ws_next, const float *W_final,
-                   int32_t act, float *hidden, float *as8, float *score,
-                   int32_t prev_ld /* floats per h_prev row, 0 = hidden_dim */,
-                   int32_t out_ld /* floats per hidden row, 0 = hidden_dim; > hidden_dim = PACKED rows:
-                                     as8 is written into the row at [hidden_dim, hidden_dim+8) and the
-                                     as8 argument only enables the projection */,
-                   void *stream);
+                   int32_t act, float *hidden, float *as8, float *score, void *stream);
 
 /* Training forward of the same node update (tensor-core kernel, hidden_dim <= 48): applies the
  * caller's dropout mask (models.py:82; values 0 or 1/(1-p), NULL = no dropout) between act(W_h agg)

@@ -31,7 +31,7 @@ class RgSegments(C.Structure):
     _fields_ = [("mode", C.c_int32), ("n_ent", C.c_int32), ("n_seg", C.c_int64), ("n_seg_dev", C.c_void_p),
                 ("seg_query", C.c_void_p), ("seg_ptr", C.c_void_p), ("adj", C.c_void_p),
                 ("seg_ent", C.c_void_p), ("ent_ptr", C.c_void_p), ("peer_dict", C.c_void_p),
-                ("peer_qinfo", C.c_void_p), ("n_table_rows", C.c_int32), ("hidden_ld", C.c_int32)]
+                ("peer_qinfo", C.c_void_p), ("n_table_rows", C.c_int32)]
 
 
 class RgHeavy(C.Structure):
@@ -54,8 +54,7 @@ SIGNATURES = {
     "rg_frontier_nodes": (C.c_int, [C.POINTER(RgFrontier), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rg_frontier_remap": (C.c_int, [C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
-    "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 3
-                       + [C.c_int32, C.c_int32, C.c_void_p]),
+    "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 4),
     "rg_node_update_train": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 9 + [C.c_int32] + [C.c_void_p] * 4),
     "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 8),
     "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),

@@ -129,9 +129,6 @@ __device__ __forceinline__ void fwd_range(const rg_segments &S, int q, int lo, i
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int cbase = complete_base_of<IMPLICIT>(S, q);
-    // packed rows (S.hidden_ld > 0): hidden row = [D hidden | 8 as8 | pad] with that stride
-    const int h_ld = S.hidden_ld > 0 ? S.hidden_ld : D, as_ld = S.hidden_ld > 0 ? S.hidden_ld : 8;
-    if (S.hidden_ld > 0) as8 = hidden + D;
 
     for (int base = lo; base < hi; base += 32) {
         const int slot = base + lane;
@@ -153,11 +150,11 @@ __device__ __forceinline__ void fwd_range(const rg_segments &S, int q, int lo, i
                 float2 z = SMEM_TAB ? reinterpret_cast<const float2 *>(s_ar8 + r * 8)[ql]
                                     : __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
                 if (HAS_HIDDEN) {
-                    const float4 *hp = reinterpret_cast<const float4 *>(hidden + (size_t)p * h_ld);
+                    const float4 *hp = reinterpret_cast<const float4 *>(hidden + (size_t)p * D);
                     float4 h[NV];
 #pragma unroll
                     for (int v = 0; v < NV; ++v) h[v] = ldg4(hp + v * 4 + ql);
-                    float2 a = __ldg(reinterpret_cast<const float2 *>(as8 + (size_t)p * as_ld) + ql);
+                    float2 a = __ldg(reinterpret_cast<const float2 *>(as8 + (size_t)p * 8) + ql);
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
                         float4 t = SMEM_TAB ? rp[v * 4 + ql] : ldg4(rp + v * 4 + ql);
@@ -267,118 +264,6 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
         fwd_range<D, HAS_HIDDEN, true, true>(S, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, acc, s_rela,
                                              s_ar8);
         store_row<D>(agg + (size_t)seg * D, acc, lane);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Packed-row persistent forward (inference, D = 48): hidden rows are 64 floats
-// [48 hidden | 8 as8 | 8 pad] (256 B, line aligned) and the shared-memory relation table rows are 56
-// floats [48 rela | 8 ar8].  8 lanes own one edge: each of the two 128-bit load instructions covers
-// exactly ONE 128-byte line of the row, so a row + its attention values cost 2 L1 wavefronts
-// (4-lane mapping: 3 + 1) and the table row 2 conflict-free LDS wavefronts.  4 edges per warp step.
-// ------------------------------------------------------------------------------------------
-constexpr int kPackedLd = 64;   // floats per packed hidden row
-constexpr int kTabLd = 56;      // floats per packed relation-table row
-
-template <bool HAS_HIDDEN>
-__global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p8(rg_segments S, const float *__restrict__ hidden,
-                                                                const float *__restrict__ rela,
-                                                                const float *__restrict__ ar8,
-                                                                const float *__restrict__ aq8,
-                                                                const float *__restrict__ w8,
-                                                                const float *__restrict__ b_alpha,
-                                                                float *__restrict__ agg, rg_heavy H, int has_heavy) {
-    constexpr int D = 48;
-    extern __shared__ __align__(16) float s_tab[];
-    const int rows = S.n_table_rows;
-    for (int i = threadIdx.x; i < rows * 14; i += kPWarps * 32) {   // 14 float4 per packed table row
-        const int r = i / 14, c = i % 14;
-        reinterpret_cast<float4 *>(s_tab)[i] = c < 12 ? __ldg(reinterpret_cast<const float4 *>(rela) + r * 12 + c)
-                                                      : __ldg(reinterpret_cast<const float4 *>(ar8) + r * 2 + (c - 12));
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, grp = lane >> 3, l8 = lane & 7;
-    const bool second = l8 < 6;                  // lanes that take part in the second load (float4 8..13)
-    const bool att = (l8 == 4) | (l8 == 5);      // ... of which these two carry as8 / ar8
-    const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
-    const float ba = __ldg(b_alpha);
-    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (att) w4 = __ldg(reinterpret_cast<const float4 *>(w8) + (l8 - 4));
-    const int We = rg_words_ent(S.n_ent);
-    for (int64_t seg = (int64_t)blockIdx.x * kPWarps + (threadIdx.x >> 5); seg < n_true;
-         seg += (int64_t)gridDim.x * kPWarps) {
-        SegRange r = seg_range<true>(S, seg);
-        int hi = r.hi;
-        if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
-            enqueue_heavy(H, seg, r.hi - r.lo, lane);
-            hi = r.lo + RG_HEAVY_CHUNK;
-        }
-        float4 aq4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (att) aq4 = __ldg(reinterpret_cast<const float4 *>(aq8 + (size_t)r.q * 8) + (l8 - 4));
-        const uint2 *drow = reinterpret_cast<const uint2 *>(S.peer_dict) + (size_t)r.q * We;
-        const int cbase = complete_base_of<true>(S, r.q);
-        float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
-        for (int base = r.lo; base < hi; base += 32) {
-            const int slot = base + lane;
-            Slot s = probe_slot<true>(S, drow, cbase, slot, slot < hi);
-            const unsigned m = __ballot_sync(RG_FULL_MASK, s.active);
-            const int cnt = __popc(m);
-#pragma unroll 2
-            for (int it = 0; it < cnt; it += 4) {
-                const int k = it + grp;
-                const bool on = k < cnt;
-                const int src = on ? ((m == RG_FULL_MASK) ? k : rg_select_low(m, k)) : 0;
-                const int p = __shfl_sync(RG_FULL_MASK, s.peer, src);
-                const int rr = __shfl_sync(RG_FULL_MASK, s.rel, src);
-                float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
-                if (on) {
-                    const float4 *tp = reinterpret_cast<const float4 *>(s_tab) + rr * 14;
-                    x0 = tp[l8];
-                    if (second) x1 = tp[8 + l8];
-                    if (HAS_HIDDEN) {
-                        const float4 *hp = reinterpret_cast<const float4 *>(hidden) + (size_t)p * (kPackedLd / 4);
-                        const float4 h0 = ldg4(hp + l8);
-                        x0 = make_float4(x0.x + h0.x, x0.y + h0.y, x0.z + h0.z, x0.w + h0.w);
-                        if (second) {
-                            const float4 h1 = ldg4(hp + 8 + l8);
-                            x1 = make_float4(x1.x + h1.x, x1.y + h1.y, x1.z + h1.z, x1.w + h1.w);
-                        }
-                    }
-                }
-                float part = 0.f;
-                if (att)
-                    part = w4.x * fmaxf(x1.x + aq4.x, 0.f) + w4.y * fmaxf(x1.y + aq4.y, 0.f) +
-                           w4.z * fmaxf(x1.z + aq4.z, 0.f) + w4.w * fmaxf(x1.w + aq4.w, 0.f);
-                part += __shfl_xor_sync(RG_FULL_MASK, part, 1);               // lanes 4 <-> 5
-                float alpha = sigmoidf_(part + ba);                            // meaningful on lanes 4 / 5
-                alpha = __shfl_sync(RG_FULL_MASK, alpha, (lane & 24) | 4);     // broadcast inside the 8-lane group
-                if (!on) alpha = 0.f;
-                acc0.x = fmaf(alpha, x0.x, acc0.x);
-                acc0.y = fmaf(alpha, x0.y, acc0.y);
-                acc0.z = fmaf(alpha, x0.z, acc0.z);
-                acc0.w = fmaf(alpha, x0.w, acc0.w);
-                acc1.x = fmaf(alpha, x1.x, acc1.x);
-                acc1.y = fmaf(alpha, x1.y, acc1.y);
-                acc1.z = fmaf(alpha, x1.z, acc1.z);
-                acc1.w = fmaf(alpha, x1.w, acc1.w);
-            }
-        }
-#pragma unroll
-        for (int o = 8; o < 32; o <<= 1) {
-            acc0.x += __shfl_xor_sync(RG_FULL_MASK, acc0.x, o);
-            acc0.y += __shfl_xor_sync(RG_FULL_MASK, acc0.y, o);
-            acc0.z += __shfl_xor_sync(RG_FULL_MASK, acc0.z, o);
-            acc0.w += __shfl_xor_sync(RG_FULL_MASK, acc0.w, o);
-            acc1.x += __shfl_xor_sync(RG_FULL_MASK, acc1.x, o);
-            acc1.y += __shfl_xor_sync(RG_FULL_MASK, acc1.y, o);
-            acc1.z += __shfl_xor_sync(RG_FULL_MASK, acc1.z, o);
-            acc1.w += __shfl_xor_sync(RG_FULL_MASK, acc1.w, o);
-        }
-        if (grp == 0) {
-            float4 *o = reinterpret_cast<float4 *>(agg + (size_t)seg * D);
-            o[l8] = acc0;                         // floats 0..31
-            if (l8 < 4) o[8 + l8] = acc1;         // floats 32..47
-        }
     }
 }
 
@@ -646,25 +531,7 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
     if (seg->n_seg == 0) return RG_OK;
     const size_t tab_bytes = (size_t)seg->n_table_rows * (D + 8) * sizeof(float);
     bool persistent = false;
-    if constexpr (IM && D == 48) {
-        const size_t ptab = (size_t)seg->n_table_rows * kTabLd * sizeof(float);
-        if (seg->hidden_ld == kPackedLd && seg->n_table_rows > 0 && ptab <= 110 * 1024) {
-            auto kern = k_edge_fwd_p8<HH>;
-            RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptab));
-            int dev = 0, n_sm = 148, per_sm = 1;
-            RG_CUDA_CALL(cudaGetDevice(&dev));
-            RG_CUDA_CALL(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-            RG_CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPWarps * 32, ptab));
-            if (per_sm >= 1) {
-                const unsigned grid = (unsigned)std::min<int64_t>(rg_cdiv(seg->n_seg, kPWarps), (int64_t)n_sm * per_sm);
-                kern<<<grid, kPWarps * 32, ptab, st>>>(*seg, hidden, rela, ar8, aq8, w8, b_alpha, agg, H, has_heavy);
-                RG_LAUNCH_CHECK();
-                persistent = true;
-            }
-        }
-    }
     if constexpr (IM) {
-        if (persistent) goto heavy_pass;
         // relation tables staged in shared memory when two 16-warp CTAs still fit one SM
         if (seg->n_table_rows > 0 && tab_bytes <= 110 * 1024 && seg->n_seg >= 4096) {
             auto kern = k_edge_fwd_p<D, HH>;
@@ -689,7 +556,6 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
                                                        has_heavy);
         RG_LAUNCH_CHECK();
     }
-heavy_pass:
     if (has_heavy) {
         k_edge_fwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, H);
         RG_LAUNCH_CHECK();
@@ -742,11 +608,7 @@ int rg_edge_agg_fwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
     rc = check_heavy(heavy);
     if (rc) return rc;
     if (!rela || !ar8 || !aq8 || !w8 || !b_alpha || !agg) return RG_ERR_BAD_ARG;
-    if (seg->hidden_ld > 0) {  // packed rows carry as8 themselves
-        if (seg->hidden_ld < hidden_dim + 8 || seg->hidden_ld % 4 || as8 != nullptr) return RG_ERR_BAD_ARG;
-    } else if ((hidden == nullptr) != (as8 == nullptr)) {
-        return RG_ERR_BAD_ARG;
-    }
+    if ((hidden == nullptr) != (as8 == nullptr)) return RG_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const bool hh = hidden != nullptr, im = seg->mode == 1;
 #define RG_FWD(HH, IM) \

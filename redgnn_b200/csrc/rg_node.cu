@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kThreads) k_node_update(
     const float *__restrict__ W_h, const float *__restrict__ W_ih, const float *__restrict__ W_hh,
     const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ Ws_next,
     const float *__restrict__ W_final, int act, int64_t n_nodes_host, const int64_t *__restrict__ n_nodes_dev,
-    float *__restrict__ hidden, float *__restrict__ as8, float *__restrict__ score, int prev_ld, int out_ld) {
+    float *__restrict__ hidden, float *__restrict__ as8, float *__restrict__ score) {
     extern __shared__ float sm[];
     const int64_t n_nodes = n_nodes_dev ? *n_nodes_dev : n_nodes_host;
     using L = NodeSmem<D>;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) k_node_update(
                 a = __ldg(reinterpret_cast<const float4 *>(agg + (size_t)(row0 + r) * D) + v);
                 if (HAS_H0) {
                     const int s = __ldg(src + row0 + r);
-                    if (s >= 0) h = __ldg(reinterpret_cast<const float4 *>(h_prev + (size_t)s * prev_ld) + v);
+                    if (s >= 0) h = __ldg(reinterpret_cast<const float4 *>(h_prev + (size_t)s * D) + v);
                 }
             }
             float *pa = sm + L::A + r * S + v * 4;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) k_node_update(
                     const float h0 = HAS_H0 ? sm[L::H0 + r * S + c] : 0.f;
                     const float hn = (1.0f - zg) * ng + zg * h0;
                     sm[L::A + r * S + c] = hn;
-                    if (r < rows) hidden[(size_t)(row0 + r) * out_ld + c] = hn;
+                    if (r < rows) hidden[(size_t)(row0 + r) * D + c] = hn;
                 }
             }
         }
@@ -208,12 +208,8 @@ __global__ void __launch_bounds__(kThreads) k_node_update(
                 float s = 0.f;
 #pragma unroll 8
                 for (int k = 0; k < D; ++k) s = fmaf(ph[k], pw[k], s);
-                if (a < 8) {
-                    if (out_ld > D)
-                        hidden[(size_t)(row0 + r) * out_ld + D + a] = s;   // packed rows
-                    else
-                        as8[(size_t)(row0 + r) * 8 + a] = s;
-                }
+                if (a < 8)
+                    as8[(size_t)(row0 + r) * 8 + a] = s;
                 else
                     score[row0 + r] = s;
             }
@@ -226,7 +222,7 @@ template <int D, bool HH>
 int launch_node(const float *agg, const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                 const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                 const float *W_final, int act, int64_t n_nodes, const int64_t *n_nodes_dev, float *hidden,
-                float *as8, float *score, int prev_ld, int out_ld, cudaStream_t st) {
+                float *as8, float *score, cudaStream_t st) {
     constexpr size_t smem = sizeof(float) * NodeSmem<D>::Total;
     auto kern = k_node_update<D, HH>;
     RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -238,7 +234,7 @@ int launch_node(const float *agg, const float *h_prev, const int32_t *src, const
     const int64_t n_tiles = (n_nodes + kTM - 1) / kTM;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)n_sm * per_sm);
     kern<<<grid, kThreads, smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
-                                       n_nodes, n_nodes_dev, hidden, as8, score, prev_ld, out_ld);
+                                       n_nodes, n_nodes_dev, hidden, as8, score);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -356,7 +352,7 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
                       const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                       const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                       const float *W_final, int32_t act, float *hidden, float *as8, float *score,
-                      const float *drop_mask, float *saved, int32_t prev_ld, int32_t out_ld, cudaStream_t st);
+                      const float *drop_mask, float *saved, cudaStream_t st);
 
 // elementwise part of the GRU-cell backward (the GEMMs around it are plain library calls).
 // One CTA = kGruRows consecutive nodes x all D columns (thread = (row lane, column)); besides the
@@ -448,20 +444,14 @@ extern "C" int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const i
     if (hidden_dim > 48) return RG_ERR_UNSUPPORTED;
     if (n_nodes == 0) return RG_OK;
     return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, nullptr,
-                             nullptr, act, hidden, nullptr, nullptr, drop_mask, saved, hidden_dim, hidden_dim,
-                             (cudaStream_t)stream);
+                             nullptr, act, hidden, nullptr, nullptr, drop_mask, saved, (cudaStream_t)stream);
 }
 
 extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
                               const float *h_prev,
                               const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                               const float *b_ih, const float *b_hh, const float *Ws_next, const float *W_final,
-                              int32_t act, float *hidden, float *as8, float *score, int32_t prev_ld,
-                              int32_t out_ld, void *stream) {
-    if (prev_ld <= 0) prev_ld = hidden_dim;
-    if (out_ld <= 0) out_ld = hidden_dim;
-    if (prev_ld < hidden_dim || out_ld < hidden_dim || prev_ld % 4 || out_ld % 4) return RG_ERR_BAD_ARG;
-    if (as8 && out_ld > hidden_dim && out_ld < hidden_dim + 8) return RG_ERR_BAD_ARG;
+                              int32_t act, float *hidden, float *as8, float *score, void *stream) {
     if (n_nodes < 0 || !agg || !W_h || !W_ih || !W_hh || !b_ih || !b_hh || !hidden) return RG_ERR_BAD_ARG;
     if ((h_prev == nullptr) != (src == nullptr)) return RG_ERR_BAD_ARG;
     if ((as8 != nullptr) != (Ws_next != nullptr) || (score != nullptr) != (W_final != nullptr)) return RG_ERR_BAD_ARG;
@@ -473,12 +463,12 @@ extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t
     const char *force_simt = std::getenv("REDGNN_NODE_SIMT");
     if (hidden_dim <= 48 && !(force_simt && force_simt[0] == '1'))
         return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh,
-                                 Ws_next, W_final, act, hidden, as8, score, nullptr, nullptr, prev_ld, out_ld, st);
+                                 Ws_next, W_final, act, hidden, as8, score, nullptr, nullptr, st);
 #define RG_NODE(DD)                                                                                              \
     return h_prev ? launch_node<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,   \
-                                          n_nodes, n_nodes_dev, hidden, as8, score, prev_ld, out_ld, st)                                       \
+                                          n_nodes, n_nodes_dev, hidden, as8, score, st)                                       \
                   : launch_node<DD, false>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,  \
-                                           n_nodes, n_nodes_dev, hidden, as8, score, prev_ld, out_ld, st)
+                                           n_nodes, n_nodes_dev, hidden, as8, score, st)
     switch (hidden_dim) {
         case 16: RG_NODE(16);
         case 32: RG_NODE(32);

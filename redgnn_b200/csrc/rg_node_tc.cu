@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
     const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ Ws_next,
     const float *__restrict__ W_final, int act, int64_t n_nodes_host, const int64_t *__restrict__ n_nodes_dev,
     float *__restrict__ hidden, float *__restrict__ as8, float *__restrict__ score,
-    const float *__restrict__ drop_mask, float *__restrict__ saved, int prev_ld, int out_ld) {
+    const float *__restrict__ drop_mask, float *__restrict__ saved) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using L = TcSmem<D>;
     constexpr int KC = L::KC;
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
             const float4 *pa = reinterpret_cast<const float4 *>(agg + (size_t)(live ? row : 0) * D);
             int s = -1;
             if (HAS_H0 && live) s = __ldg(src + row);
-            const float4 *ph = reinterpret_cast<const float4 *>(h_prev + (size_t)(s >= 0 ? s : 0) * prev_ld);
+            const float4 *ph = reinterpret_cast<const float4 *>(h_prev + (size_t)(s >= 0 ? s : 0) * D);
             float4 a[4], h[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                 }
             }
             if (live) {
-                float4 *po = reinterpret_cast<float4 *>(hidden + (size_t)row * out_ld + c0);
+                float4 *po = reinterpret_cast<float4 *>(hidden + (size_t)row * D + c0);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) po[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
             }
@@ -368,9 +368,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                         proj[a] = sacc;
                     }
                     if (as8) {
-                        // packed rows (out_ld > D): the projection rides in the hidden row at [D, D+8)
-                        float4 *po = out_ld > D ? reinterpret_cast<float4 *>(hidden + (size_t)row * out_ld + D)
-                                                : reinterpret_cast<float4 *>(as8 + (size_t)row * 8);
+                        float4 *po = reinterpret_cast<float4 *>(as8 + (size_t)row * 8);
                         po[0] = make_float4(proj[0], proj[1], proj[2], proj[3]);
                         po[1] = make_float4(proj[4], proj[5], proj[6], proj[7]);
                     }
@@ -389,8 +387,7 @@ template <int D, bool HH>
 int launch_node_tc(const float *agg, const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                    const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                    const float *W_final, int act, int64_t n_nodes, const int64_t *n_nodes_dev, float *hidden,
-                   float *as8, float *score, const float *drop_mask, float *saved, int prev_ld, int out_ld,
-                   cudaStream_t st) {
+                   float *as8, float *score, const float *drop_mask, float *saved, cudaStream_t st) {
     constexpr size_t smem = TcSmem<D>::TOTAL;
     static_assert(smem <= 232448, "tile does not fit the 227 KB shared memory of one CTA");
     auto kern = k_node_update_tc<D, HH>;
@@ -401,7 +398,7 @@ int launch_node_tc(const float *agg, const float *h_prev, const int32_t *src, co
     const int64_t n_tiles = (n_nodes + kTcRows - 1) / kTcRows;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);  // persistent: one CTA per SM
     kern<<<grid, 128 * (D / 16), smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
-                                         n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, prev_ld, out_ld);
+                                         n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -414,16 +411,12 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
                       const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                       const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                       const float *W_final, int32_t act, float *hidden, float *as8, float *score,
-                      const float *drop_mask, float *saved, int32_t prev_ld, int32_t out_ld, cudaStream_t st) {
-    if (prev_ld <= 0) prev_ld = hidden_dim;
-    if (out_ld <= 0) out_ld = hidden_dim;
+                      const float *drop_mask, float *saved, cudaStream_t st) {
 #define RG_NODE_TC(DD)                                                                                             \
     return h_prev ? launch_node_tc<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,  \
-                                             n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, prev_ld,  \
-                                             out_ld, st)                                                          \
+                                             n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, st)       \
                   : launch_node_tc<DD, false>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act, \
-                                              n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, prev_ld, \
-                                              out_ld, st)
+                                              n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, st)
     switch (hidden_dim) {
         case 16: RG_NODE_TC(16);
         case 32: RG_NODE_TC(32);

@@ -136,7 +136,6 @@ class RedGNN(torch.nn.Module):
     # once into a CUDA graph and replayed: the ~100 launches / allocations of a forward cost one
     # cudaGraphLaunch instead of milliseconds of host time.
     use_cuda_graph = True
-    packed_rows = True
     inference_in_eval = True
     fused_train_node_update = True     # autograd path: node update in the tcgen05 kernel (hidden_dim <= 48)
     MAX_CACHED_GRAPHS = 4
@@ -223,11 +222,9 @@ class RedGNN(torch.nn.Module):
             ws_next = None if last else F.pad(self.gnn_layers[i + 1].Ws_attn.weight,
                                               (0, 0, 0, 8 - self.attn_dim)).contiguous()
             src = fr.inverse_remap_to(fr_next, cap) if hidden is not None else None
-            # d = 48: packed 64-float rows [hidden | as8 | pad] feed the 8-lane edge kernel of the next layer
-            out_ld = 64 if (self.packed_rows and d == 48 and not last) else 0
             hidden, as8, scores = node_update(agg, hidden, src, layer.W_h.weight, self.gate,
                                               ACT_CODES[self.act_name], ws_next,
-                                              self.W_final.weight if last else None, n_dev=n_dev, out_ld=out_ld)
+                                              self.W_final.weight if last else None, n_dev=n_dev)
             frontiers.append(fr_next)
             fr = fr_next
         self._last_stats = frontiers                      # resolved lazily by `last_stats`

@@ -25,7 +25,6 @@ class Segments(object):
         self.n_seg_dev = None      # optional int64 device scalar: true segment count (n_seg = upper bound)
         self.peer_qinfo = None     # implicit: per-query {base, count} of the peer frontier
         self.n_table_rows = 0      # 2R+1 when known: lets the forward kernel stage rela / ar8 in smem
-        self.hidden_ld = 0         # > 0: packed hidden rows [D hidden | 8 as8 | pad] of that many floats
         self._c = None
 
     @staticmethod
@@ -68,7 +67,7 @@ class Segments(object):
                                       self.ent_ptr.data_ptr() if self.ent_ptr is not None else None,
                                       self.peer_dict.data_ptr() if self.peer_dict is not None else None,
                                       self.peer_qinfo.data_ptr() if self.peer_qinfo is not None else None,
-                                      self.n_table_rows, self.hidden_ld)
+                                      self.n_table_rows)
         return self._c
 
 
@@ -99,9 +98,8 @@ def edge_agg_forward(fwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha):
     """Raw launcher (no autograd): returns agg [n_seg, D]."""
     _lib.require_cuda(rela, ar8, aq8, w8, b_alpha, hidden, as8)
     d = rela.shape[1]
-    hidden_ld = hidden.shape[1] if (hidden is not None and hidden.shape[1] != d) else 0   # packed rows
-    if fwd_seg.n_table_rows != rela.shape[0] or fwd_seg.hidden_ld != hidden_ld:
-        fwd_seg.n_table_rows, fwd_seg.hidden_ld, fwd_seg._c = rela.shape[0], hidden_ld, None
+    if fwd_seg.n_table_rows != rela.shape[0]:
+        fwd_seg.n_table_rows, fwd_seg._c = rela.shape[0], None
     agg = torch.empty((fwd_seg.n_seg, d), dtype=torch.float32, device=rela.device)
     heavy = _Heavy(fwd_seg.heavy_bound, d, rela.device)
     with _lib.Stats.timed("edge_fwd", (fwd_seg, d, hidden is not None)):
@@ -146,26 +144,21 @@ def scatter_scores(node_b, node_e, score, n_query, n_ent_out, n_dev=None):
     return out
 
 
-def node_update(agg, h_prev, src, W_h, gate, act_code, Ws_next8=None, W_final=None, n_dev=None, out_ld=0):
+def node_update(agg, h_prev, src, W_h, gate, act_code, Ws_next8=None, W_final=None, n_dev=None):
     """Fused inference node update (rg_node_update): returns (hidden, as8 | None, score | None).
-    gate: the nn.GRU module (weight_ih_l0 [3D,D], weight_hh_l0, bias_ih_l0, bias_hh_l0).
-    out_ld > D: PACKED output rows [D hidden | 8 as8 | pad] of out_ld floats (as8 returned as None);
-    h_prev may itself be packed (its row length is taken from its shape)."""
+    gate: the nn.GRU module (weight_ih_l0 [3D,D], weight_hh_l0, bias_ih_l0, bias_hh_l0)."""
     _lib.require_cuda(agg, h_prev, src, W_h)
     n, d = agg.shape
-    packed = out_ld > d
-    prev_ld = h_prev.shape[1] if h_prev is not None else 0
-    hidden = torch.empty((n, out_ld if packed else d), dtype=torch.float32, device=agg.device)
-    as8 = torch.empty((1 if packed else n, 8), dtype=torch.float32, device=agg.device) if Ws_next8 is not None \
-        else None
+    hidden = torch.empty((n, d), dtype=torch.float32, device=agg.device)
+    as8 = torch.empty((n, 8), dtype=torch.float32, device=agg.device) if Ws_next8 is not None else None
     score = torch.empty((n,), dtype=torch.float32, device=agg.device) if W_final is not None else None
     with _lib.Stats.timed("node_update", (n, d)):
         check(lib.rg_node_update(d, n, ptr(n_dev), ptr(agg), ptr(h_prev), ptr(src), ptr(_f32c(W_h)), ptr(_f32c(gate.weight_ih_l0)),
                                  ptr(_f32c(gate.weight_hh_l0)), ptr(_f32c(gate.bias_ih_l0)),
                                  ptr(_f32c(gate.bias_hh_l0)), ptr(Ws_next8), ptr(_f32c(W_final)), act_code,
-                                 ptr(hidden), ptr(as8), ptr(score), prev_ld, out_ld if packed else 0, stream_ptr()))
+                                 ptr(hidden), ptr(as8), ptr(score), stream_ptr()))
     _lib.Stats.launches += 1
-    return hidden, (None if packed else as8), score
+    return hidden, as8, score
 
 
 class NodeUpdateTrain(torch.autograd.Function):

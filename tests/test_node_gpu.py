@@ -68,25 +68,3 @@ def test_node_update_variants(d, n, act, has_h0):
     with torch.no_grad():
         part = node_update(agg, h_prev, src, W_h, gru, act, Ws8, W_final, n_dev=n_true)
     assert torch.equal(part[0][:n // 3], outs["tc" if d <= 48 else "simt"][0][:n // 3])
-
-
-def test_packed_rows_round_trip():
-    """Packed 64-float rows [48 hidden | 8 as8 | pad]: same values as the separate outputs, and a
-    packed h_prev is read with its own row stride."""
-    from redgnn_b200.ops import node_update
-    torch.manual_seed(0)
-    dev, d, n, n_prev = "cuda", 48, 700, 300
-    agg = torch.randn(n, d, device=dev)
-    W_h = torch.randn(d, d, device=dev) / d ** 0.5
-    gru = torch.nn.GRU(d, d).to(dev)
-    Ws8 = F.pad(torch.randn(5, d, device=dev) / d ** 0.5, (0, 0, 0, 3)).contiguous()
-    h_prev = torch.randn(n_prev, d, device=dev)
-    h_prev_packed = torch.zeros(n_prev, 64, device=dev)
-    h_prev_packed[:, :d] = h_prev
-    src = torch.full((n,), -1, dtype=torch.int32, device=dev)
-    src[torch.randperm(n, device=dev)[:n_prev].sort()[0]] = torch.arange(n_prev, dtype=torch.int32, device=dev)
-    with torch.no_grad():
-        hid, as8, _ = node_update(agg, h_prev, src, W_h, gru, 1, Ws8, None)
-        packed, none, _ = node_update(agg, h_prev_packed, src, W_h, gru, 1, Ws8, None, out_ld=64)
-    assert none is None and packed.shape == (n, 64)
-    assert torch.equal(packed[:, :d], hid) and torch.equal(packed[:, d:d + 8], as8)
