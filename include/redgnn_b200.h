@@ -127,6 +127,16 @@ size_t rg_frontier_emask_bytes(int32_t n_query, int32_t n_ent);
 size_t rg_frontier_dict_bytes(int32_t n_query, int32_t n_ent);
 size_t rg_workspace_bytes(int32_t n_query, int32_t n_ent, int64_t n_fact);
 
+/* Graph build: the CSR views of rg_graph from the fact arrays (replaces the scipy csr_matrix of
+ * load_graph, transductive/load_data.py:76-81, re-run every epoch by shuffle_train :152-164).
+ * head/rel/tail: device int32 [n_fact] in reference row order INCLUDING the self-loop block.
+ * Outputs (caller-allocated): in_ptr/out_ptr [n_ent+1], in_adj/out_adj [n_fact][2]; rows are stable
+ * in fact order.  Every entity id must lie in [0, n_ent). */
+size_t rg_graph_build_workspace_bytes(int32_t n_ent, int64_t n_fact);
+int rg_graph_build(const int32_t *head, const int32_t *rel, const int32_t *tail, int32_t n_ent,
+                   int64_t n_fact, int32_t *in_ptr, int32_t *in_adj, int32_t *out_ptr, int32_t *out_adj,
+                   void *ws, size_t ws_bytes, void *stream);
+
 /* ---- expansion: DataLoader.get_neighbors (transductive/load_data.py:106-131,
  *      inductive/load_data.py:115-143) --------------------------------------------------------- */
 

@@ -47,6 +47,8 @@ SIGNATURES = {
     "rg_frontier_emask_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rg_frontier_dict_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rg_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "rg_graph_build_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
+    "rg_graph_build": (C.c_int, [C.c_void_p] * 3 + [C.c_int32, C.c_int64] + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
     "rg_frontier_from_nodes": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(RgFrontier), C.c_void_p,
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
     "rg_frontier_step": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier),

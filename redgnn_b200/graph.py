@@ -38,8 +38,24 @@ class DeviceGraph(object):
         self.n_ent, self.n_rel, self.n_fact = int(n_ent), int(n_rel), int(kg.shape[0])
         h, r, t = kg[:, 0].contiguous(), kg[:, 1].contiguous(), kg[:, 2].contiguous()
         self.head, self.rel, self.tail = (x.to(torch.int32).contiguous() for x in (h, r, t))
-        self.in_ptr, self.in_adj, in_deg = _csr(t, h, r, n_ent)
-        self.out_ptr, self.out_adj, out_deg = _csr(h, t, r, n_ent)
+        if self.device.type == 'cuda':
+            # device build through the C ABI (stable radix sort of the fact ids by tail / by head)
+            i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=self.device)
+            self.in_ptr, self.in_adj = i32(n_ent + 1), i32(self.n_fact, 2)
+            self.out_ptr, self.out_adj = i32(n_ent + 1), i32(self.n_fact, 2)
+            with torch.cuda.device(self.device):
+                ws = torch.empty(lib.rg_graph_build_workspace_bytes(n_ent, self.n_fact), dtype=torch.uint8,
+                                 device=self.device)
+                check(lib.rg_graph_build(ptr(self.head), ptr(self.rel), ptr(self.tail), n_ent, self.n_fact,
+                                         ptr(self.in_ptr), ptr(self.in_adj), ptr(self.out_ptr), ptr(self.out_adj),
+                                         ptr(ws), ws.numel(), stream_ptr()))
+            in_deg = (self.in_ptr[1:] - self.in_ptr[:-1]).long()
+            out_deg = (self.out_ptr[1:] - self.out_ptr[:-1]).long()
+        else:
+            # host-side construction of the same arrays (data preparation only; used by the CPU tests of
+            # the loaders -- every kernel entry point still requires CUDA tensors)
+            self.in_ptr, self.in_adj, in_deg = _csr(t, h, r, n_ent)
+            self.out_ptr, self.out_adj, out_deg = _csr(h, t, r, n_ent)
         ck = _lib.RG_HEAVY_CHUNK
         # per-query upper bounds for the heavy-segment queues of the edge kernels
         self.heavy_in = (int(((in_deg - 1) // ck).sum()), int((in_deg > ck).sum()))

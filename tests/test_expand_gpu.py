@@ -126,3 +126,17 @@ def test_size_independent_properties_at_scale():
         assert all(torch.equal(a, b) for a, b in zip((tn, ed, rm), again))    # deterministic
         del fact_key, key_in
         nodes = tn
+
+
+@pytest.mark.parametrize("fixture", ["tiny_dir", "hub_dir"])
+def test_graph_build_matches_host_construction(request, fixture):
+    """rg_graph_build (device radix sort) against the host construction of the same CSR views."""
+    from redgnn_b200 import DeviceGraph
+    from helpers import graph_triples
+    D = O.TransductiveData(request.getfixturevalue(fixture))
+    tri = graph_triples(D.test_graph)
+    g_dev = DeviceGraph(tri, D.n_ent, D.n_rel, "cuda")
+    g_cpu = DeviceGraph(tri, D.n_ent, D.n_rel, "cpu")
+    for name in ("head", "rel", "tail", "in_ptr", "in_adj", "out_ptr", "out_adj"):
+        assert torch.equal(getattr(g_dev, name).cpu(), getattr(g_cpu, name)), name
+    assert g_dev.heavy_in == g_cpu.heavy_in and g_dev.heavy_out == g_cpu.heavy_out
