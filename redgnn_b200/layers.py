@@ -254,9 +254,10 @@ class RedGNN(torch.nn.Module):
         need_grad = torch.is_grad_enabled() and (self.training or not self.inference_in_eval)
         if not need_grad and not (self.training and self.dropout.p > 0) and n > 0 \
                 and n * graph.n_ent * (d + 10) * 4 * 4 <= self.ASYNC_BUDGET_BYTES:
-            if self.use_cuda_graph and _lib.Stats.timing is None:
-                return self._run_graph(q_sub, q_rel, graph, n_ent_out)
-            return self._run_async(q_sub, q_rel, graph, n_ent_out)
+            with torch.no_grad():    # eval() with autograd on still lands here (inference_in_eval)
+                if self.use_cuda_graph and _lib.Stats.timing is None:
+                    return self._run_graph(q_sub, q_rel, graph, n_ent_out)
+                return self._run_async(q_sub, q_rel, graph, n_ent_out)
         if need_grad and self.graph_train and d <= 48 and n > 0 and _lib.Stats.timing is None \
                 and n * graph.n_ent * d * 4 * 9 * self.n_layer <= self.ASYNC_BUDGET_BYTES:
             return self._run_train_graph(q_sub, q_rel, graph, n_ent_out)
