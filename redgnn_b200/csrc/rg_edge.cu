@@ -241,14 +241,41 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
                                                                const float *__restrict__ w8,
                                                                const float *__restrict__ b_alpha,
                                                                float *__restrict__ agg, rg_heavy H, int has_heavy) {
-    extern __shared__ __align__(16) float s_tab[];
+    extern __shared__ __align__(128) float s_tab[];
+    __shared__ __align__(8) unsigned long long tab_bar;
     const int rows = S.n_table_rows;
     float *s_rela = s_tab, *s_ar8 = s_tab + (size_t)rows * D;
-    for (int i = threadIdx.x; i < rows * D / 4; i += kPWarps * 32)
-        reinterpret_cast<float4 *>(s_rela)[i] = __ldg(reinterpret_cast<const float4 *>(rela) + i);
-    for (int i = threadIdx.x; i < rows * 2; i += kPWarps * 32)
-        reinterpret_cast<float4 *>(s_ar8)[i] = __ldg(reinterpret_cast<const float4 *>(ar8) + i);
-    __syncthreads();
+    // stage both tables with the TMA bulk-copy engine (cp.async.bulk, 1-D): one elected thread issues
+    // two copies that complete on an mbarrier; no thread spends issue slots on the 100 KB transfer
+    if (threadIdx.x == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tab_bar);
+        const uint32_t bytes_rela = (uint32_t)rows * D * 4, bytes_ar8 = (uint32_t)rows * 32;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_rela + bytes_ar8)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(s_rela)),
+                     "l"(rela), "r"(bytes_rela), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(s_ar8)),
+                     "l"(ar8), "r"(bytes_ar8), "r"(bar)
+                     : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tab_bar);
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n}"
+                : "=r"(ok)
+                : "r"(bar)
+                : "memory");
+    }
     const int lane = threadIdx.x & 31;
     const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
     const float ba = __ldg(b_alpha);
