@@ -77,12 +77,13 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region: the poller is started early
+    (nvidia-smi needs ~0.2 s before its first row) and only rows stamped inside [begin, end] count."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
 
     def start(self):
         try:
@@ -96,18 +97,29 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        rows = [r for t, r in self.rows if len(r) >= 7 and t0 <= t <= t1 + 0.03]
+        if not rows:                                   # region shorter than the polling period: nearest rows
+            rows = [r for t, r in self.rows if len(r) >= 7 and t >= t0 - 0.05][:3]
+        num = lambda x: x.replace(".", "").isdigit()
+        sm = [float(r[1]) for r in rows if num(r[1])]
+        mx = [float(r[2]) for r in rows if num(r[2])]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k].lower().startswith("active")
-                                                         for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -301,22 +313,24 @@ def main():
     for i in range(n_steps_total):
         b = step_batch(0, i)
         dev_batches.append(tuple(torch.as_tensor(b[:, c].astype(np.int64)).to(dev) for c in range(3)))
-    for i in range(args.warmup):
-        run_step(*dev_batches[i])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        run_step(*dev_batches[i])
+    barrier()
     _lib.Stats.launches = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     edges_total = 0
     barrier()
+    sampler.begin()
     for i in range(args.steps):
         flush.zero_()                                   # L2 flush between timed iterations (untimed)
         ev[i][0].record()
         run_step(*dev_batches[args.warmup + i])
         ev[i][1].record()
     barrier()
+    sampler.end()
     launches = _lib.Stats.launches
     clocks = sampler.stop() if rank == 0 else None
     t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
