@@ -424,3 +424,46 @@ def test_edge_case_batches(tiny_dir):
     out = model(subs[:1], rels[:1])
     out.sum().backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+
+
+def test_optimizer_steps_track_the_oracle(tiny_dir):
+    """Five Adam steps of the reference training recipe (sum loss, weight decay; base_model.py:27,49-62)
+    run through the oracle on the CPU and through the CUDA path from the same initialisation:
+    the loss sequences agree step by step (gradients are right, parameters stay in sync)."""
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    L, D = TransductiveLoader(tiny_dir), O.TransductiveData(tiny_dir)
+    sd0 = O.init_state_dict(3, 48, 5, D.n_rel, seed=21)
+    batches = [L.get_batch(np.arange(k * 10, (k + 1) * 10)) for k in range(5)]
+    # oracle loop
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    opt = torch.optim.Adam(list(sd.values()), lr=3e-3, weight_decay=1e-5)
+    want = []
+    for tri in batches:
+        opt.zero_grad()
+        loss = O.train_loss(O.model_forward(sd, D.graph, tri[:, 0], tri[:, 1], 3, "relu"), tri[:, 2])
+        loss.backward()
+        opt.step()
+        want.append(float(loss.detach()))
+    # CUDA loop (graph-captured training step)
+    model = RED_GNN_trans(Options(hidden_dim=48, attn_dim=5, n_layer=3, dropout=0.0, act="relu", n_rel=L.n_rel), L).cuda()
+    model.load_state_dict(sd0)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=3e-3, weight_decay=1e-5)
+    got = []
+    for tri in batches:
+        opt.zero_grad()
+        got.append(float(cuda_loss_backward_train(model, tri).detach()))
+        opt.step()
+    rel = np.abs(np.array(got) - np.array(want)) / np.abs(np.array(want))
+    assert rel.max() < 5e-4, (got, want)
+    for k, p in model.named_parameters():
+        assert_close(p, sd[k], 2e-3, "parameter after 5 steps " + k)
+
+
+def cuda_loss_backward_train(model, tri):
+    out = model(tri[:, 0], tri[:, 1])
+    pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
+    mx = out.max(1, keepdim=True)[0]
+    loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1)))
+    loss.backward()
+    return loss
