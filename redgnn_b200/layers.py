@@ -68,6 +68,8 @@ class GNNLayer(torch.nn.Module):
         """models.py:23-43 for a caller-provided edge list
         edges[E,6] = (batch_idx, head, rela, tail, old_idx, new_idx)."""
         _lib.require_cuda(hidden, edges)
+        if edges.shape[0] == 0:      # no messages at all: scatter() of nothing is zeros (models.py:39-41)
+            return self.act(self.W_h(torch.zeros((int(n_node), self.in_dim), device=hidden.device)))
         sub, rel, obj, r_idx = edges[:, 4], edges[:, 2], edges[:, 5], edges[:, 0]
         fwd_seg = Segments.explicit(obj, sub, rel, r_idx, int(n_node))
         bwd_seg = Segments.explicit(sub, obj, rel, r_idx, int(hidden.shape[0])) if torch.is_grad_enabled() else None

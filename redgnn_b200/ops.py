@@ -90,6 +90,19 @@ class _Heavy(object):
         return C.byref(self.struct) if self.struct is not None else None
 
 
+# debugging aid (tests): synchronise after every edge kernel and fail if a heavy-segment queue
+# overflowed its statically computed capacity (which would silently drop chunks)
+DEBUG_CHECK_HEAVY = False
+
+
+def _check_heavy(heavy, what):
+    if DEBUG_CHECK_HEAVY and heavy.struct is not None:
+        c = heavy.counters.cpu()
+        if int(c[2]) != 0 or int(c[0]) > heavy.max_chunks or int(c[1]) > heavy.max_nodes:
+            raise _lib.RgError("%s: heavy-segment queue overflow (chunks %d/%d, nodes %d/%d)" % (
+                what, int(c[0]), heavy.max_chunks, int(c[1]), heavy.max_nodes))
+
+
 def _f32c(t):
     return None if t is None else t.detach().to(torch.float32).contiguous()
 
@@ -106,6 +119,7 @@ def edge_agg_forward(fwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha):
         check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
                                   ptr(aq8), ptr(w8), ptr(b_alpha), ptr(agg), heavy.ref(), stream_ptr()))
     _lib.Stats.launches += 3 if heavy.struct is not None else 1
+    _check_heavy(heavy, "rg_edge_agg_fwd")
     return agg
 
 
@@ -124,6 +138,7 @@ def edge_agg_backward(bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, 
                                   ptr(aq8), ptr(w8), ptr(b_alpha), ptr(g_agg), ptr(g_hidden), ptr(node_small),
                                   ptr(g_rela), ptr(g_ar8), heavy.ref(), stream_ptr()))
     _lib.Stats.launches += 3 if heavy.struct is not None else 1
+    _check_heavy(heavy, "rg_edge_agg_bwd")
     g_as8 = node_small[:, :8]
     g_aq8 = torch.zeros((n_query, 8), dtype=torch.float32, device=dev)
     g_aq8.index_add_(0, bwd_seg.seg_query.long(), g_as8)

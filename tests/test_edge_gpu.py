@@ -8,6 +8,16 @@ from oracle import redgnn_oracle as O
 from helpers import device_graph, assert_close, assert_grad_close, to64
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _check_heavy_queues():
+    from redgnn_b200 import ops
+    ops.DEBUG_CHECK_HEAVY = True
+    yield
+    ops.DEBUG_CHECK_HEAVY = False
+
+
 ACT = {"relu": torch.relu, "tanh": torch.tanh, "idd": lambda x: x}
 
 
@@ -142,3 +152,11 @@ def test_implicit_matches_explicit(request, fixture, extra_hops):
     grads_imp = torch.autograd.grad((out_imp * w).sum(), [h_imp] + list(layer.parameters()))
     for ge, gi, name in zip(grads_exp, grads_imp, ["hidden"] + [k for k, _ in layer.named_parameters()]):
         assert_close(gi, ge, 1e-4, "implicit grad " + name)
+
+
+def test_layer_with_no_edges():
+    layer, sd = make_layer(48, 5, 4, "tanh", seed=6)
+    hidden = torch.randn(3, 48, device="cuda")
+    out = layer(None, torch.tensor([0, 1, 2]).cuda(), hidden, torch.zeros((0, 6), dtype=torch.long, device="cuda"), 7,
+                None)
+    assert out.shape == (7, 48) and float(out.abs().max()) == 0.0

@@ -47,7 +47,7 @@ def test_golden_fb237_v2_inductive():
             nodes = tn.cpu().numpy()
 
 
-@pytest.mark.parametrize("n_query", [1, 5, 32, 33, 70, 200])
+@pytest.mark.parametrize("n_query", [1, 5, 32, 33, 70, 200, 1000])
 def test_synthetic_vs_oracle(tiny_dir, n_query):
     D = O.TransductiveData(tiny_dir)
     g = D.test_graph
