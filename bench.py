@@ -339,11 +339,10 @@ def main():
     # an instrumented pass over the SAME batches (the timed region above replays CUDA graphs, which
     # cannot hold event records).  Algorithmic bytes per launch:
     #   (16 + 4d) * E + 4d * N'   with the hidden-row gather (layers >= 1),  16 * E + 4d * N' at layer 0
-    if hasattr(model, "use_cuda_graph"):              # warm the eager path (allocator pools) untimed
-        model.use_cuda_graph = False
-        run_step(*dev_batches[0])
-        model.use_cuda_graph = True
-        barrier()
+    _lib.Stats.timing = []                            # routes every step through the eager, instrumented path
+    for i in range(2):                                # untimed warm-up of exactly that path (allocator pools)
+        run_step(*dev_batches[i])
+    barrier()
     _lib.Stats.timing = []
     for i in range(args.steps):
         flush.zero_()
