@@ -350,10 +350,18 @@ def main():
         edges_total += sum(model.last_stats["edges"])
     barrier()
     timing, _lib.Stats.timing = _lib.Stats.timing, None
-    edge_ms, edge_bytes = 0.0, 0.0
+    edge_ms, edge_bytes, bwd_ms, bwd_bytes = 0.0, 0.0, 0.0, 0.0
     kernel_ms = {}
     for name, meta, a, b in timing:
         kernel_ms[name] = kernel_ms.get(name, 0.0) + a.elapsed_time(b) / args.steps
+        if name == "edge_bwd":
+            # push backward over the CSR-by-head: 16 B of structure per edge, the g_agg row of the tail node
+            # per edge (4d), the hidden row of the head segment once per segment plus the g_hidden row written
+            # (8d per head node, layers >= 1); alpha is recomputed, not stored
+            seg, d, has_hidden = meta
+            n_seg, e_l = seg.n_seg, seg.n_edges or 0
+            bwd_ms += a.elapsed_time(b)
+            bwd_bytes += (16 + 4 * d) * e_l + (8 * d if has_hidden else 0) * n_seg
         if name != "edge_fwd":
             continue
         seg, d, has_hidden = meta
@@ -362,6 +370,41 @@ def main():
         edge_ms += a.elapsed_time(b)
         edge_bytes += ((16 + 4 * d) if has_hidden else 16) * e_l + 4 * d * n_seg
     t_instr = edge_ms * 1e-3
+
+    # subsystem (1): the drop-in get_neighbors chain (explicit sampled_edges / tail_nodes / remap emission,
+    # reference load_data.py:106-131) over the first timed batch, device time per hop between CUDA events
+    # (the 16-byte count read-back between them is excluded).  Bytes: SURVEY 8(d) B_exp.
+    kg = loader.graph_for(mode, dev)
+    exp_ms, exp_emit_ms, exp_bytes, exp_edges = 0.0, 0.0, 0.0, 0
+    for rep in range(2):                                  # rep 0 = warm-up (allocator), rep 1 = measured
+        subs0 = dev_batches[args.warmup][0]
+        nodes = torch.stack([torch.arange(batch, device=dev), subs0], 1)
+        spans = []
+        for l in range(n_layer):
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
+            fr_in = kg.frontier_from_nodes(nodes, batch)
+            fr_out = kg.step(fr_in)
+            e1.record()
+            n_in, n_e, n_out, _ = fr_out.read_counts(also=fr_in)
+            if (n_e + n_out) * 48 > (40 << 30):           # keep the explicit edge list within HBM
+                break
+            e2.record()
+            tail_nodes = fr_out.nodes64(n_out)
+            remap = fr_in.remap_to(fr_out, n_in)
+            edges = kg.emit_edges(fr_in, fr_out, n_e)
+            e3.record()
+            spans.append((e0, e1, e2, e3, 56 * n_e + 4 * kg.n_fact + 24 * n_in + 16 * n_out, n_e))
+            nodes = tail_nodes
+            del edges, remap
+        torch.cuda.synchronize()
+        if rep == 1:
+            for e0, e1, e2, e3, nbytes, n_e in spans:
+                exp_ms += e0.elapsed_time(e1) + e2.elapsed_time(e3)
+                exp_emit_ms += e2.elapsed_time(e3)
+                exp_bytes += nbytes
+                exp_edges += n_e
+    del nodes, tail_nodes
 
     # ---------------- end-to-end timing through the public API with host buffers (e2e) ----------------
     host_batches = [step_batch(1, i) for i in range(n_steps_total)]
@@ -410,7 +453,8 @@ def main():
         if tj.get("workload") == args.workload:
             traffic = tj["traffic_bytes_per_launch"]
     qps = world * batch * args.steps / t_dev
-    achieved = (edge_bytes / 1e9) / (edge_ms * 1e-3) if edge_ms > 0 else 0.0
+    gbps = lambda nbytes, ms: (nbytes / 1e9) / (ms * 1e-3) if ms > 0 else 0.0
+    achieved = gbps(edge_bytes, edge_ms)
     line = {
         "metric": "queries/s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
@@ -430,6 +474,19 @@ def main():
                      "traffic": traffic, "peak_source": peak_src, "share_of_step": t_instr / t_dev,
                      "timing": "CUDA events around every rg_edge_agg_fwd launch, instrumented pass over the same batches",
                      "bytes_model": "(16+4d)*E + 4d*N' per launch (16*E + 4d*N' at layer 0)"},
+        "subsystems": {
+            "expand": {"kernels": "rg_frontier_from_nodes + rg_frontier_step + rg_frontier_nodes + rg_frontier_remap "
+                                  "+ rg_edges_emit (explicit get_neighbors outputs, %d hops, one batch)" % n_layer,
+                       "ms": exp_ms, "ms_emit_part": exp_emit_ms, "edges": exp_edges, "achieved": gbps(exp_bytes, exp_ms), "peak": peak,
+                       "unit": "GB/s", "frac": gbps(exp_bytes, exp_ms) / peak,
+                       "bytes_model": "56*E + 4*n_fact + 24*N + 16*N' per hop"},
+            "edge_fwd": {"ms_per_step": edge_ms / args.steps, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak},
+            "edge_bwd": None if not args.train else {
+                "ms_per_step": bwd_ms / args.steps, "achieved": gbps(bwd_bytes, bwd_ms), "peak": peak,
+                "unit": "GB/s", "frac": gbps(bwd_bytes, bwd_ms) / peak,
+                "bytes_model": "(16+4d)*E + 8d*N per launch (16+4d)*E at layer 0"},
+        },
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:

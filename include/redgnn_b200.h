@@ -100,7 +100,7 @@ typedef struct rg_segments {
     const int32_t *ent_ptr;        /* implicit: [n_ent+1]                                      */
     const uint32_t *peer_dict;     /* implicit: [n_query][We][2]                               */
     const int32_t *peer_qinfo;     /* implicit, optional: rg_frontier.qinfo of the peer frontier     */
-    int32_t n_table_rows;          /* rows of the relation tables (2R+1); > 0 lets the forward kernel
+    int32_t n_table_rows;          /* rows of the relation tables (2R+1); > 0 lets the edge kernels
                                       stage rela / ar8 in shared memory when they fit            */
 } rg_segments;
 
@@ -187,12 +187,15 @@ int rg_edge_agg_fwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
  *   node_small[p] = { g_as8[p][0..7], sum_e g_l*relu(z)[0..7], sum_e g_l, 7 x 0 }   ([N][24])
  *   g_rela[r]    += sum_e alpha_e * g_agg[s_e]     (fp32 atomics into a caller-zeroed buffer)
  *   g_ar8[r]     += sum_e g_z,e                    (fp32 atomics into a caller-zeroed buffer)
- * with g_l = <g_agg[s], hidden[p]+rela[r]> * alpha(1-alpha), g_z = g_l * w8 * [z > 0]. */
+ * with g_l = <g_agg[s], hidden[p]+rela[r]> * alpha(1-alpha), g_z = g_l * w8 * [z > 0].
+ * grad_copies >= 1: g_rela is [grad_copies][n_table_rows][D] and g_ar8 [grad_copies][n_table_rows][8]
+ * (needs seg->n_table_rows > 0 when > 1); CTAs spread their atomics over the copies and the caller
+ * sums them -- the few thousand accumulator sectors otherwise serialise in L2. */
 int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hidden,
                     const float *as8, const float *rela, const float *ar8, const float *aq8,
                     const float *w8, const float *b_alpha, const float *g_agg, float *g_hidden,
-                    float *node_small, float *g_rela, float *g_ar8, const rg_heavy *heavy,
-                    void *stream);
+                    float *node_small, float *g_rela, float *g_ar8, int32_t grad_copies,
+                    const rg_heavy *heavy, void *stream);
 
 /* ---- node update: models.py:41 (act(W_h agg)), :81 (h0 re-index), :83 (single-step nn.GRU, gate
  *      order r,z,n; dropout :82 is the identity in eval mode), next layer's Ws_attn(hidden) and

@@ -7,11 +7,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libredgnn_b200.so")
+LIB_PATH = os.environ.get("REDGNN_B200_LIB") or os.path.join(_HERE, "libredgnn_b200.so")   # env: developer builds
 
 RG_ABI_VERSION = 1
 RG_COUNTS_WORDS = 8
 RG_CNT_N_IN, RG_CNT_E, RG_CNT_N_OUT, RG_CNT_ERR = 0, 1, 2, 3
+GRAD_COPIES = int(os.environ.get("REDGNN_GRAD_COPIES", "8"))   # relation-gradient accumulator replicas
 RG_HEAVY_CHUNK = 512
 
 
@@ -69,7 +70,7 @@ SIGNATURES = {
     "rg_edge_agg_fwd": (C.c_int, [C.POINTER(RgSegments), C.c_int32] + [C.c_void_p] * 8
                         + [C.POINTER(RgHeavy), C.c_void_p]),
     "rg_edge_agg_bwd": (C.c_int, [C.POINTER(RgSegments), C.c_int32] + [C.c_void_p] * 12
-                        + [C.POINTER(RgHeavy), C.c_void_p]),
+                        + [C.c_int32, C.POINTER(RgHeavy), C.c_void_p]),
 }
 
 

@@ -226,11 +226,46 @@ __global__ void __launch_bounds__(kBlock, 5) k_edge_fwd(rg_segments S, const flo
     store_row<D>(agg + (size_t)seg * D, acc, lane);
 }
 
+// Stage the two relation tables in shared memory with the TMA bulk-copy engine (cp.async.bulk, 1-D):
+// one elected thread issues two copies that complete on an mbarrier; no thread spends issue slots
+// on the ~100 KB transfer.  Block-collective (contains a __syncthreads).
+__device__ __forceinline__ void stage_tables(unsigned long long *tab_bar, float *s_a, const float *g_a,
+                                             uint32_t bytes_a, float *s_b, const float *g_b, uint32_t bytes_b) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(tab_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_a + bytes_b)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(s_a)),
+                     "l"(g_a), "r"(bytes_a), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(s_b)),
+                     "l"(g_b), "r"(bytes_b), "r"(bar)
+                     : "memory");
+    }
+    __syncthreads();  // the barrier is initialised before anyone polls it
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar)
+            : "memory");
+}
+
 // Persistent variant for the implicit (model) path: 16 warps per CTA, CTAs sized to the SM count,
 // the relation tables (rela [rows][D], ar8 [rows][8]) staged once per CTA in shared memory so the
 // per-edge relation row comes from LDS (half the L1 wavefronts of the global path), segments
 // handed out round-robin (warp w of CTA c takes c*16+w, then += grid*16).
-constexpr int kPWarps = 16;
+#ifndef RG_PWARPS
+#define RG_PWARPS 16
+#endif
+constexpr int kPWarps = RG_PWARPS;
 
 template <int D, bool HAS_HIDDEN>
 __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, const float *__restrict__ hidden,
@@ -245,37 +280,7 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
     __shared__ __align__(8) unsigned long long tab_bar;
     const int rows = S.n_table_rows;
     float *s_rela = s_tab, *s_ar8 = s_tab + (size_t)rows * D;
-    // stage both tables with the TMA bulk-copy engine (cp.async.bulk, 1-D): one elected thread issues
-    // two copies that complete on an mbarrier; no thread spends issue slots on the 100 KB transfer
-    if (threadIdx.x == 0) {
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tab_bar);
-        const uint32_t bytes_rela = (uint32_t)rows * D * 4, bytes_ar8 = (uint32_t)rows * 32;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes_rela + bytes_ar8)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         (uint32_t)__cvta_generic_to_shared(s_rela)),
-                     "l"(rela), "r"(bytes_rela), "r"(bar)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         (uint32_t)__cvta_generic_to_shared(s_ar8)),
-                     "l"(ar8), "r"(bytes_ar8), "r"(bar)
-                     : "memory");
-    }
-    __syncthreads();  // the barrier is initialised before anyone polls it
-    {
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tab_bar);
-        uint32_t ok = 0;
-        while (!ok)
-            asm volatile(
-                "{\n.reg .pred p;\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
-                "selp.u32 %0, 1, 0, p;\n}"
-                : "=r"(ok)
-                : "r"(bar)
-                : "memory");
-    }
+    stage_tables(&tab_bar, s_rela, rela, (uint32_t)rows * D * 4, s_ar8, ar8, (uint32_t)rows * 32);
     const int lane = threadIdx.x & 31;
     const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
     const float ba = __ldg(b_alpha);
@@ -351,13 +356,14 @@ struct BwdSmall {
     float gl;
 };
 
-template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+template <int D, bool HAS_HIDDEN, bool IMPLICIT, bool SMEM_TAB = false>
 __device__ __forceinline__ void bwd_range(const rg_segments &S, int64_t seg, int q, int lo, int hi,
                                           const float *__restrict__ hidden, const float *__restrict__ as8,
                                           const float *__restrict__ rela, const float *__restrict__ ar8,
                                           const float *__restrict__ aq8, const float *__restrict__ w8,
                                           float b_alpha, const float *__restrict__ g_agg, float *g_rela,
-                                          float *g_ar8, float4 (&G)[D / 16], BwdSmall &sm) {
+                                          float *g_ar8, float4 (&G)[D / 16], BwdSmall &sm,
+                                          const float *s_rela = nullptr, const float *s_ar8 = nullptr) {
     constexpr int NV = D / 16;
     const int lane = threadIdx.x & 31, grp = lane >> 2, ql = lane & 3;
     const float2 w2 = __ldg(reinterpret_cast<const float2 *>(w8) + ql);
@@ -398,13 +404,15 @@ __device__ __forceinline__ void bwd_range(const rg_segments &S, int64_t seg, int
             float dot = 0.f, part = 0.f;
             if (on) {
                 const float4 *gp = reinterpret_cast<const float4 *>(g_agg + (size_t)p * D);
-                const float4 *rp = reinterpret_cast<const float4 *>(rela + (size_t)r * D);
+                const float4 *rp = SMEM_TAB ? reinterpret_cast<const float4 *>(s_rela + r * D)
+                                            : reinterpret_cast<const float4 *>(rela + (size_t)r * D);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) g[v] = ldg4(gp + v * 4 + ql);
-                float2 a = __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
+                float2 a = SMEM_TAB ? reinterpret_cast<const float2 *>(s_ar8 + r * 8)[ql]
+                                    : __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
-                    float4 t = ldg4(rp + v * 4 + ql);
+                    float4 t = SMEM_TAB ? rp[v * 4 + ql] : ldg4(rp + v * 4 + ql);
                     dot = fmaf(g[v].x, hs[v].x + t.x, dot);
                     dot = fmaf(g[v].y, hs[v].y + t.y, dot);
                     dot = fmaf(g[v].z, hs[v].z + t.z, dot);
@@ -438,9 +446,13 @@ __device__ __forceinline__ void bwd_range(const rg_segments &S, int64_t seg, int
                     G[v].y += ag.y;
                     G[v].z += ag.z;
                     G[v].w += ag.w;
+#ifndef RG_EXP_NO_RELA_RED
                     atomicAdd(gr + v * 4 + ql, ag);
+#endif
                 }
+#ifndef RG_EXP_NO_AR8_RED
                 atomicAdd(reinterpret_cast<float2 *>(g_ar8 + (size_t)r * 8) + ql, gz);
+#endif
             }
         }
     }
@@ -461,6 +473,18 @@ __device__ __forceinline__ void bwd_range(const rg_segments &S, int64_t seg, int
     }
 }
 
+// The relation-gradient accumulators may be replicated (`copies` > 1, [copies][rows][D] and
+// [copies][rows][8]): a CTA adds into copy blockIdx % copies, which spreads the fp32 reductions of
+// the few thousand hot sectors over `copies` times as many L2 lines; the caller sums the copies.
+template <int D>
+__device__ __forceinline__ void select_copy(float *&g_rela, float *&g_ar8, int copies, int rows) {
+    if (copies > 1) {
+        const size_t c = blockIdx.x % (unsigned)copies;
+        g_rela += c * (size_t)rows * D;
+        g_ar8 += c * (size_t)rows * 8;
+    }
+}
+
 // node_small row layout: [0..7] g_as8, [8..15] sum g_l*relu(z), [16] sum g_l, [17..23] zero
 __device__ __forceinline__ void store_small(float *dst, const BwdSmall &sm, int lane) {
     if (lane < 4) {
@@ -477,9 +501,10 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
                                                      const float *__restrict__ ar8, const float *__restrict__ aq8,
                                                      const float *__restrict__ w8, const float *__restrict__ b_alpha,
                                                      const float *__restrict__ g_agg, float *g_hidden,
-                                                     float *node_small, float *g_rela, float *g_ar8, rg_heavy H,
-                                                     int has_heavy) {
+                                                     float *node_small, float *g_rela, float *g_ar8, int copies,
+                                                     rg_heavy H, int has_heavy) {
     const int lane = threadIdx.x & 31;
+    select_copy<D>(g_rela, g_ar8, copies, S.n_table_rows);
     const int64_t seg = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (seg >= (S.n_seg_dev ? *S.n_seg_dev : S.n_seg)) return;
     SegRange r = seg_range<IMPLICIT>(S, seg);
@@ -496,6 +521,45 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
     store_small(node_small + (size_t)seg * 24, sm, lane);
 }
 
+// Persistent variant (implicit path): warps loop over segments on their own, so a block never idles
+// behind its longest segment, and the relation tables are read from shared memory (see k_edge_fwd_p).
+template <int D, bool HAS_HIDDEN>
+__global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_bwd_p(rg_segments S, const float *__restrict__ hidden,
+                                                               const float *__restrict__ as8,
+                                                               const float *__restrict__ rela,
+                                                               const float *__restrict__ ar8,
+                                                               const float *__restrict__ aq8,
+                                                               const float *__restrict__ w8,
+                                                               const float *__restrict__ b_alpha,
+                                                               const float *__restrict__ g_agg, float *g_hidden,
+                                                               float *node_small, float *g_rela, float *g_ar8,
+                                                               int copies, rg_heavy H, int has_heavy) {
+    extern __shared__ __align__(128) float s_tab[];
+    __shared__ __align__(8) unsigned long long tab_bar;
+    select_copy<D>(g_rela, g_ar8, copies, S.n_table_rows);
+    const int rows = S.n_table_rows;
+    float *s_rela = s_tab, *s_ar8 = s_tab + (size_t)rows * D;
+    stage_tables(&tab_bar, s_rela, rela, (uint32_t)rows * D * 4, s_ar8, ar8, (uint32_t)rows * 32);
+    const int lane = threadIdx.x & 31;
+    const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
+    const float ba = __ldg(b_alpha);
+    for (int64_t seg = (int64_t)blockIdx.x * kPWarps + (threadIdx.x >> 5); seg < n_true;
+         seg += (int64_t)gridDim.x * kPWarps) {
+        SegRange r = seg_range<true>(S, seg);
+        int hi = r.hi;
+        if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
+            enqueue_heavy(H, seg, r.hi - r.lo, lane);
+            hi = r.lo + RG_HEAVY_CHUNK;
+        }
+        float4 G[D / 16];
+        BwdSmall sm;
+        bwd_range<D, HAS_HIDDEN, true, true>(S, seg, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, g_agg, g_rela,
+                                             g_ar8, G, sm, s_rela, s_ar8);
+        if (g_hidden) store_row<D>(g_hidden + (size_t)seg * D, G, lane);
+        store_small(node_small + (size_t)seg * 24, sm, lane);
+    }
+}
+
 template <int D, bool HAS_HIDDEN, bool IMPLICIT>
 __global__ void __launch_bounds__(kBlock) k_edge_bwd_chunks(rg_segments S, const float *__restrict__ hidden,
                                                             const float *__restrict__ as8,
@@ -505,8 +569,9 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd_chunks(rg_segments S, const
                                                             const float *__restrict__ w8,
                                                             const float *__restrict__ b_alpha,
                                                             const float *__restrict__ g_agg, float *g_rela,
-                                                            float *g_ar8, rg_heavy H) {
+                                                            float *g_ar8, int copies, rg_heavy H) {
     const int lane = threadIdx.x & 31;
+    select_copy<D>(g_rela, g_ar8, copies, S.n_table_rows);
     if (H.counters[2]) return;
     const int n_chunks = min(H.counters[0], H.max_chunks);
     const int stride = gridDim.x * kWarpsPerBlock;
@@ -595,18 +660,40 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
 template <int D, bool HH, bool IM>
 int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, const float *rela, const float *ar8,
                const float *aq8, const float *w8, const float *b_alpha, const float *g_agg, float *g_hidden,
-               float *node_small, float *g_rela, float *g_ar8, const rg_heavy *heavy, cudaStream_t st) {
+               float *node_small, float *g_rela, float *g_ar8, int copies, const rg_heavy *heavy, cudaStream_t st) {
     rg_heavy H = {};
     const int has_heavy = heavy && heavy->max_chunks > 0 && heavy->max_nodes > 0;
     if (has_heavy) H = *heavy;
     if (seg->n_seg == 0) return RG_OK;
-    const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
-    k_edge_bwd<D, HH, IM><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, g_hidden,
-                                                   node_small, g_rela, g_ar8, H, has_heavy);
-    RG_LAUNCH_CHECK();
+    const size_t tab_bytes = (size_t)seg->n_table_rows * (D + 8) * sizeof(float);
+    bool persistent = false;
+    if constexpr (IM) {
+        if (seg->n_table_rows > 0 && tab_bytes <= 110 * 1024 && seg->n_seg >= 4096) {
+            auto kern = k_edge_bwd_p<D, HH>;
+            RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+            int dev = 0, n_sm = 148, per_sm = 1;
+            RG_CUDA_CALL(cudaGetDevice(&dev));
+            RG_CUDA_CALL(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            RG_CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPWarps * 32, tab_bytes));
+            if (per_sm >= 1) {
+                const int64_t want = rg_cdiv(seg->n_seg, kPWarps);
+                const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)n_sm * per_sm);
+                kern<<<grid, kPWarps * 32, tab_bytes, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,
+                                                            g_hidden, node_small, g_rela, g_ar8, copies, H, has_heavy);
+                RG_LAUNCH_CHECK();
+                persistent = true;
+            }
+        }
+    }
+    if (!persistent) {
+        const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
+        k_edge_bwd<D, HH, IM><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, g_hidden,
+                                                       node_small, g_rela, g_ar8, copies, H, has_heavy);
+        RG_LAUNCH_CHECK();
+    }
     if (has_heavy) {
         k_edge_bwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha,
-                                                                    g_agg, g_rela, g_ar8, H);
+                                                                    g_agg, g_rela, g_ar8, copies, H);
         RG_LAUNCH_CHECK();
         k_heavy_fixup<<<kHeavyGrid, kBlock, 0, st>>>(H, D + 24, g_hidden, D, node_small, 24);
         RG_LAUNCH_CHECK();
@@ -651,7 +738,7 @@ int rg_edge_agg_fwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
 int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hidden, const float *as8,
                     const float *rela, const float *ar8, const float *aq8, const float *w8, const float *b_alpha,
                     const float *g_agg, float *g_hidden, float *node_small, float *g_rela, float *g_ar8,
-                    const rg_heavy *heavy, void *stream) {
+                    int32_t grad_copies, const rg_heavy *heavy, void *stream) {
     int rc = check_segments(seg);
     if (rc) return rc;
     rc = check_heavy(heavy);
@@ -660,11 +747,13 @@ int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
         return RG_ERR_BAD_ARG;
     if ((hidden == nullptr) != (as8 == nullptr)) return RG_ERR_BAD_ARG;
     if (!hidden && g_hidden) return RG_ERR_BAD_ARG;
+    if (grad_copies < 1 || (grad_copies > 1 && seg->n_table_rows <= 0)) return RG_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const bool hh = hidden != nullptr, im = seg->mode == 1;
 #define RG_BWD(HH, IM)                                                                                             \
     RG_DISPATCH_D(hidden_dim, rc = (launch_bwd<DD, HH, IM>(seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,   \
-                                                           g_hidden, node_small, g_rela, g_ar8, heavy, st)))
+                                                           g_hidden, node_small, g_rela, g_ar8, grad_copies,   \
+                                                           heavy, st)))
     if (hh && im) { RG_BWD(true, true); }
     else if (hh && !im) { RG_BWD(true, false); }
     else if (!hh && im) { RG_BWD(false, true); }

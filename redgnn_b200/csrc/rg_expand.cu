@@ -178,18 +178,38 @@ __global__ void __launch_bounds__(kBlock) k_remap(const uint32_t *__restrict__ d
     }
 }
 
-// emit sampled_edges[E][6] in reference order; one block = one tile of 1024 fact rows
+// emit sampled_edges[E][6] in reference order (fact ascending, batch index descending).
+// blockIdx.x = tile of RG_TILE fact rows; the kEmitParts blocks of blockIdx.y share the tile: each
+// rebuilds the tile's edge offsets (cheap next to the edges) and its warps take every
+// (8 * kEmitParts)-th fact.  A fact's edges differ only in the query: lane l of a warp owns query
+// w*32 + 31 - l of mask word w, so the row position is a popcount (no search), the rows are built
+// in shared memory and leave as coalesced 16-byte pieces of one contiguous run.  Queries whose
+// frontier is complete (qinfo count == n_ent) skip the dictionary probe: rank = base + entity.
+constexpr int kEmitParts = 4;
+
+__device__ __forceinline__ int emit_complete_base(const int32_t *qinfo, int b, int n_query, int n_ent) {
+    if (qinfo == nullptr || b >= n_query) return -1;
+    const int2 qi = __ldg(reinterpret_cast<const int2 *>(qinfo) + b);
+    return qi.y == n_ent ? qi.x : -1;
+}
+
+template <bool MASK_SMEM>  // Wn <= 2: the head's query mask and the per-lane query info are cached
 __global__ void __launch_bounds__(kBlock) k_emit_edges(const int32_t *__restrict__ head,
                                                        const int32_t *__restrict__ rel,
                                                        const int32_t *__restrict__ tail, int64_t n_fact,
                                                        const uint32_t *__restrict__ emask_in, int Wn,
                                                        const uint32_t *__restrict__ dict_in,
                                                        const uint32_t *__restrict__ dict_out, int We,
+                                                       const int32_t *__restrict__ qinfo_in,
+                                                       const int32_t *__restrict__ qinfo_out, int n_query, int n_ent,
                                                        const unsigned long long *__restrict__ blockprefix,
                                                        int64_t *edges) {
     __shared__ uint32_t s_off[RG_TILE + 1];
     __shared__ int32_t s_head[RG_TILE];
+    __shared__ int2 s_rt[RG_TILE];
+    __shared__ uint2 s_mask[MASK_SMEM ? RG_TILE : 1];
     __shared__ uint32_t sm[kBlock / 32 + 1];
+    __shared__ __align__(16) longlong2 s_rows[kBlock / 32][96];
     constexpr int IPT = RG_TILE / kBlock;
     const int64_t base = (int64_t)blockIdx.x * RG_TILE;
     const unsigned long long ebase = blockprefix[blockIdx.x];
@@ -200,24 +220,35 @@ __global__ void __launch_bounds__(kBlock) k_emit_edges(const int32_t *__restrict
         int64_t f = base + idx;
         int h = -1;
         uint32_t c = 0;
+        uint2 mk = make_uint2(0u, 0u);
+        int2 rt = make_int2(0, 0);
         if (f < n_fact) {
             h = head[f];
+            rt = make_int2(rel[f], tail[f]);
             const uint32_t *row = emask_in + (size_t)h * Wn;
-            for (int w = 0; w < Wn; ++w) c += __popc(row[w]);
+            if (MASK_SMEM) {
+                mk.x = row[0];
+                if (Wn > 1) mk.y = row[1];
+                c = __popc(mk.x) + __popc(mk.y);
+            } else {
+                for (int w = 0; w < Wn; ++w) c += __popc(row[w]);
+            }
         }
         s_head[idx] = h;
+        s_rt[idx] = rt;
+        if (MASK_SMEM) s_mask[idx] = mk;
         s_off[idx] = c;
     }
     __syncthreads();
     {
-        uint32_t a[IPT], s = 0;
+        uint32_t a[IPT], t = 0;
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             a[k] = s_off[threadIdx.x * IPT + k];
-            s += a[k];
+            t += a[k];
         }
         uint32_t tot;
-        uint32_t ex = rg_block_exclusive_scan<kBlock>(s, sm, tot);
+        uint32_t ex = rg_block_exclusive_scan<kBlock>(t, sm, tot);
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             s_off[threadIdx.x * IPT + k] = ex;
@@ -226,40 +257,53 @@ __global__ void __launch_bounds__(kBlock) k_emit_edges(const int32_t *__restrict
         if (threadIdx.x == kBlock - 1) s_off[RG_TILE] = tot;
     }
     __syncthreads();
-    const uint32_t n_tile_edges = s_off[RG_TILE];
     const uint2 *din = reinterpret_cast<const uint2 *>(dict_in);
     const uint2 *dout = reinterpret_cast<const uint2 *>(dict_out);
-    for (uint32_t el = threadIdx.x; el < n_tile_edges; el += kBlock) {
-        int lo = 0, hi = RG_TILE;  // first idx in (0, TILE] with s_off[idx] > el
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (s_off[mid] > el)
-                hi = mid;
-            else
-                lo = mid + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bitpos = 31 - lane;
+    longlong2 *my_rows = s_rows[warp];
+    int cb_in[2] = {-1, -1}, cb_out[2] = {-1, -1};
+    if (MASK_SMEM) {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            cb_in[w] = emit_complete_base(qinfo_in, w * 32 + bitpos, n_query, n_ent);
+            cb_out[w] = emit_complete_base(qinfo_out, w * 32 + bitpos, n_query, n_ent);
         }
-        const int idx = lo - 1;
-        int k = (int)(el - s_off[idx]);
-        const int64_t f = base + idx;
+    }
+    for (int idx = blockIdx.y * (kBlock / 32) + warp; idx < RG_TILE; idx += kEmitParts * (kBlock / 32)) {
+        const uint32_t off = s_off[idx];
+        if (s_off[idx + 1] == off) continue;  // warp-uniform
         const int h = s_head[idx];
-        const int r = rel[f], t = tail[f];
-        const uint32_t *row = emask_in + (size_t)h * Wn;
-        int b = 0;
+        const int2 rt = s_rt[idx];
+        longlong2 *dst = reinterpret_cast<longlong2 *>(edges + 6 * (int64_t)(ebase + off));
         for (int w = Wn - 1; w >= 0; --w) {
-            uint32_t m = row[w];
-            int c = __popc(m);
-            if (k < c) {
-                b = w * 32 + rg_select_high(m, k);
-                break;
+            uint32_t m;
+            if (MASK_SMEM)
+                m = w ? s_mask[idx].y : s_mask[idx].x;
+            else
+                m = emask_in[(size_t)h * Wn + w];
+            if (!m) continue;  // warp-uniform
+            if ((m >> bitpos) & 1u) {
+                const int k = __popc((m >> bitpos) >> 1);  // set bits above mine = rows before mine
+                const int b = w * 32 + bitpos;
+                const int ci = MASK_SMEM ? (w ? cb_in[1] : cb_in[0]) : emit_complete_base(qinfo_in, b, n_query, n_ent);
+                const int co = MASK_SMEM ? (w ? cb_out[1] : cb_out[0])
+                                         : emit_complete_base(qinfo_out, b, n_query, n_ent);
+                const uint32_t hi_idx = ci >= 0 ? (uint32_t)(ci + h) : rg_rank(din[(size_t)b * We + (h >> 5)], h);
+                const uint32_t ti_idx =
+                    co >= 0 ? (uint32_t)(co + rt.y) : rg_rank(dout[(size_t)b * We + (rt.y >> 5)], rt.y);
+                my_rows[k * 3 + 0] = make_longlong2(b, h);
+                my_rows[k * 3 + 1] = make_longlong2(rt.x, rt.y);
+                my_rows[k * 3 + 2] = make_longlong2((long long)hi_idx, (long long)ti_idx);
             }
-            k -= c;
+            __syncwarp();
+            const int n_piece = 3 * __popc(m);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (lane + 32 * j < n_piece) dst[lane + 32 * j] = my_rows[lane + 32 * j];
+            dst += n_piece;
+            __syncwarp();
         }
-        const uint32_t hi_idx = rg_rank(din[(size_t)b * We + (h >> 5)], h);
-        const uint32_t ti_idx = rg_rank(dout[(size_t)b * We + (t >> 5)], t);
-        longlong2 *dst = reinterpret_cast<longlong2 *>(edges + 6 * (int64_t)(ebase + el));
-        dst[0] = make_longlong2(b, h);
-        dst[1] = make_longlong2(r, t);
-        dst[2] = make_longlong2((long long)hi_idx, (long long)ti_idx);
     }
 }
 
@@ -404,9 +448,12 @@ int rg_edges_emit(const rg_graph *g, const rg_frontier *in, const rg_frontier *o
     RgWorkspace w = rg_carve(const_cast<void *>(ws), in->n_query, in->n_ent, g->n_fact);
     if (ws_bytes < w.total_bytes) return RG_ERR_WORKSPACE;
     const int64_t nbf = rg_cdiv(g->n_fact, RG_TILE);
-    k_emit_edges<<<(unsigned)nbf, kBlock, 0, (cudaStream_t)stream>>>(
-        g->head, g->rel, g->tail, g->n_fact, in->emask, rg_words_query(in->n_query), in->dict, out->dict,
-        rg_words_ent(in->n_ent), w.fact_blockprefix, edges);
+    const int Wn = rg_words_query(in->n_query);
+    const dim3 grid((unsigned)nbf, kEmitParts);
+    auto kern = Wn <= 2 ? k_emit_edges<true> : k_emit_edges<false>;
+    kern<<<grid, kBlock, 0, (cudaStream_t)stream>>>(g->head, g->rel, g->tail, g->n_fact, in->emask, Wn, in->dict,
+                                                    out->dict, rg_words_ent(in->n_ent), in->qinfo, out->qinfo,
+                                                    in->n_query, in->n_ent, w.fact_blockprefix, edges);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }

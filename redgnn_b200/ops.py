@@ -24,7 +24,7 @@ class Segments(object):
         self.n_edges = int(adj.shape[0]) if mode == 0 else None       # implicit: set by the caller if known
         self.n_seg_dev = None      # optional int64 device scalar: true segment count (n_seg = upper bound)
         self.peer_qinfo = None     # implicit: per-query {base, count} of the peer frontier
-        self.n_table_rows = 0      # 2R+1 when known: lets the forward kernel stage rela / ar8 in smem
+        self.n_table_rows = 0      # 2R+1 when known: lets the edge kernels stage rela / ar8 in smem
         self._c = None
 
     @staticmethod
@@ -127,16 +127,20 @@ def edge_agg_backward(bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, 
     """Raw launcher: returns (g_hidden | None, g_as8 | None, g_rela, g_ar8, g_aq8, g_w8, g_b)."""
     d = rela.shape[1]
     n_in = bwd_seg.n_seg
+    if bwd_seg.n_table_rows != rela.shape[0]:
+        bwd_seg.n_table_rows, bwd_seg._c = rela.shape[0], None
     dev = rela.device
     g_hidden = torch.empty((n_in, d), dtype=torch.float32, device=dev) if hidden is not None else None
     node_small = torch.empty((n_in, 24), dtype=torch.float32, device=dev)
-    g_rela = torch.zeros_like(rela)
-    g_ar8 = torch.zeros_like(ar8)
+    copies = _lib.GRAD_COPIES
+    g_rela = torch.zeros((copies,) + tuple(rela.shape), dtype=torch.float32, device=dev)
+    g_ar8 = torch.zeros((copies,) + tuple(ar8.shape), dtype=torch.float32, device=dev)
     heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
     with _lib.Stats.timed("edge_bwd", (bwd_seg, d, hidden is not None)):
         check(lib.rg_edge_agg_bwd(C.byref(bwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
                                   ptr(aq8), ptr(w8), ptr(b_alpha), ptr(g_agg), ptr(g_hidden), ptr(node_small),
-                                  ptr(g_rela), ptr(g_ar8), heavy.ref(), stream_ptr()))
+                                  ptr(g_rela), ptr(g_ar8), copies, heavy.ref(), stream_ptr()))
+    g_rela, g_ar8 = g_rela.sum(0), g_ar8.sum(0)
     _lib.Stats.launches += 3 if heavy.struct is not None else 1
     _check_heavy(heavy, "rg_edge_agg_bwd")
     g_as8 = node_small[:, :8]

@@ -103,6 +103,7 @@ class TrainStepRunner(object):
             fwd_seg.n_seg_dev, fwd_seg.n_table_rows = n_dev, rela.shape[0]
             bwd_seg = Segments.implicit(node_b, node_e, g.out_ptr, g.out_adj, fr_next, g.heavy_out)
             bwd_seg.n_seg_dev = n_in_dev                         # None at layer 0: exactly n query nodes
+            bwd_seg.n_table_rows = rela.shape[0]
             heavy = _Heavy(fwd_seg.heavy_bound, d, dev)
             check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
                                       ptr(aq8), ptr(w8), ptr(layer.w_alpha.bias), ptr(self.agg[i]), heavy.ref(),
@@ -179,12 +180,14 @@ class TrainStepRunner(object):
             n_seg = bwd_seg.n_seg
             node_small = z(n_seg, 24)
             g_hid_e = z(n_seg, d) if hidden_prev is not None else None
-            g_rela, g_ar8 = torch.zeros_like(rela), z(rela.shape[0], 8)
+            copies = _lib.GRAD_COPIES
+            g_rela, g_ar8 = z(copies, rela.shape[0], d), z(copies, rela.shape[0], 8)
             heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
             check(lib.rg_edge_agg_bwd(C.byref(bwd_seg.c_struct()), d, ptr(hidden_prev), ptr(lay["as8"]), ptr(rela),
                                       ptr(lay["ar8"]), ptr(lay["aq8"]), ptr(lay["w8"]), ptr(layer.w_alpha.bias),
-                                      ptr(g_agg), ptr(g_hid_e), ptr(node_small), ptr(g_rela), ptr(g_ar8), heavy.ref(),
-                                      st()))
+                                      ptr(g_agg), ptr(g_hid_e), ptr(node_small), ptr(g_rela), ptr(g_ar8), copies,
+                                      heavy.ref(), st()))
+            g_rela, g_ar8 = g_rela.sum(0), g_ar8.sum(0)
             lay["heavy_bwd"] = heavy
             # gru elementwise + edge backward (+ chunk / fix-up kernels) + query sum (+ row scatter)
             _lib.Stats.launches += 2 + (3 if heavy.struct is not None else 1)

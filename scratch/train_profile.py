@@ -38,4 +38,4 @@ from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for i in range(8, 10): step(i)
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=34, max_name_column_width=60))
