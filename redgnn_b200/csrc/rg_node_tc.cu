@@ -13,9 +13,13 @@
 //     instruction) with fp32 accumulators in TMEM columns [x | r | z | i_n | h_n];
 //   * tcgen05.commit -> mbarrier; 128 x D/16 threads then run the epilogues: warp w owns TMEM lanes
 //     32*(w%4).. (= node rows) and the 16-column slice w/4, read with tcgen05.ld.32x32b.x16, apply
-//     the gates and write hidden; the as8 / score dot products are combined through shared memory.
-//     (Splitting the columns over D/16 warps per lane quarter triples the warps that hide the
-//     staging / epilogue latency; the tile itself stays 128 rows because of the 227 KB budget.)
+//     the gates and write hidden; the as8 / score dot products are combined through spare TMEM
+//     columns.  (Splitting the columns over D/16 warps per lane quarter triples the warps that hide
+//     the epilogue latency; the tile itself stays 128 rows because of the 227 KB budget.)
+//   * the 227 KB budget leaves room for ONE set of operand tiles, so the pipeline is in registers:
+//     while GEMM 2 of a tile runs, every thread gathers its slice of the NEXT tile (agg row and the
+//     re-indexed h_prev row; the re-index entry itself is fetched two tiles ahead) and writes it
+//     into the operand tiles as soon as GEMM 2 has consumed them.
 #include "rg_common.cuh"
 
 namespace {
@@ -81,6 +85,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// store 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        :
+        : "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+          "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+          "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+          "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+          "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // shared-memory matrix descriptor: K-major, no swizzle (INTERLEAVE), sm_100 version bits
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
     extern __shared__ __align__(1024) uint8_t smem[];
     using L = TcSmem<D>;
     constexpr int KC = L::KC;
-    constexpr uint32_t kTmemCols = (5 * D <= 128) ? 128 : 256;
+    constexpr uint32_t kTmemCols = (6 * D <= 128) ? 128 : (6 * D <= 256 ? 256 : 512);  // 5D accumulators + D scratch
     constexpr int kTcThreads = 128 * (D / 16);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int trow = (warp & 3) * 32 + (tid & 31);  // node row of the tile == TMEM lane
@@ -225,37 +244,52 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
     const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0;
 
+    // this thread's slice (node row trow, 16 columns from c0) of a tile: hi / lo parts into the operand tiles
+    const int c0 = 16 * cq;
+    auto stage_slice = [&](const float4 (&a)[4], const float4 (&h)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 hi, lo;
+            split_tf32(a[q], hi, lo);
+            *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(trow, 4 * cq + q)) = hi;
+            *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(trow, 4 * cq + q)) = lo;
+            if (HAS_H0) {
+                split_tf32(h[q], hi, lo);
+                *reinterpret_cast<float4 *>(smem + L::H_HI + L::off(trow, 4 * cq + q)) = hi;
+                *reinterpret_cast<float4 *>(smem + L::H_LO + L::off(trow, 4 * cq + q)) = lo;
+            }
+        }
+    };
+    auto load_slice = [&](int64_t r, bool ok, int s, float4 (&a)[4], float4 (&h)[4]) {
+        const float4 *pa = reinterpret_cast<const float4 *>(agg + (size_t)(ok ? r : 0) * D);
+        const float4 *ph = reinterpret_cast<const float4 *>(h_prev + (size_t)(s >= 0 ? s : 0) * D);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            a[q] = ok ? __ldg(pa + 4 * cq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_H0) h[q] = (s >= 0) ? __ldg(ph + 4 * cq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto src_of = [&](int64_t r) -> int { return (HAS_H0 && r < n_nodes) ? __ldg(src + r) : -1; };
+
+    // ---- prologue: stage the first tile; the re-index entry of the following tile is fetched one tile ahead
+    //      so that the dependent h_prev[src] gather of the prefetch below starts without a round trip ----
+    int s_next;
+    {
+        const int64_t row = (int64_t)blockIdx.x * kTcRows + trow;
+        float4 a[4], h[4];
+        load_slice(row, row < n_nodes, src_of(row), a, h);
+        s_next = src_of(row + (int64_t)gridDim.x * kTcRows);
+        stage_slice(a, h);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row = tile * kTcRows + trow;
         const bool live = row < n_nodes;
-        // ---- stage this thread's slice of its node row: agg and the re-indexed previous state ----
-        {
-            const float4 *pa = reinterpret_cast<const float4 *>(agg + (size_t)(live ? row : 0) * D);
-            int s = -1;
-            if (HAS_H0 && live) s = __ldg(src + row);
-            const float4 *ph = reinterpret_cast<const float4 *>(h_prev + (size_t)(s >= 0 ? s : 0) * D);
-            float4 a[4], h[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                a[q] = live ? __ldg(pa + 4 * cq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (HAS_H0) h[q] = (s >= 0) ? __ldg(ph + 4 * cq + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 hi, lo;
-                split_tf32(a[q], hi, lo);
-                *reinterpret_cast<float4 *>(smem + L::A_HI + L::off(trow, 4 * cq + q)) = hi;
-                *reinterpret_cast<float4 *>(smem + L::A_LO + L::off(trow, 4 * cq + q)) = lo;
-                if (HAS_H0) {
-                    split_tf32(h[q], hi, lo);
-                    *reinterpret_cast<float4 *>(smem + L::H_HI + L::off(trow, 4 * cq + q)) = hi;
-                    *reinterpret_cast<float4 *>(smem + L::H_LO + L::off(trow, 4 * cq + q)) = lo;
-                }
-            }
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
+        const int64_t nrow = row + (int64_t)gridDim.x * kTcRows;  // this thread's row in the CTA's next tile
+        const bool has_next = tile + gridDim.x < n_tiles;          // block-uniform
 
         // ---- GEMM 1: x = agg . W_h^T  -> TMEM [0, D) ----
         if (tid == 0) {
@@ -268,7 +302,6 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
         tc_fence_after();
         // epilogue 1: x = act(.) back to shared memory (overwrites the agg tile) as hi / lo
         {
-            const int c0 = 16 * cq;
             float v[16];
             tmem_ld16(t_lane + c0, v);
 #pragma unroll
@@ -303,12 +336,29 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
             }
             tc_commit(bar);
         }
+        // prefetch the next tile's rows into registers: the gather latency hides behind GEMM 2
+        float4 na[4], nh[4];
+        load_slice(nrow, has_next && nrow < n_nodes, has_next ? s_next : -1, na, nh);
+        s_next = src_of(nrow + (int64_t)gridDim.x * kTcRows);
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
+        // GEMM 2 has consumed both operand tiles: take this thread's h0 slice out of the h0 tile, then
+        // overwrite the same positions of both tiles with the next tile's rows
+        float h0v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 hh = make_float4(0.f, 0.f, 0.f, 0.f), hl = hh;
+            if (HAS_H0) {
+                hh = *reinterpret_cast<const float4 *>(smem + L::H_HI + L::off(trow, c0 / 4 + q));
+                hl = *reinterpret_cast<const float4 *>(smem + L::H_LO + L::off(trow, c0 / 4 + q));
+            }
+            h0v[4 * q] = hh.x + hl.x; h0v[4 * q + 1] = hh.y + hl.y;
+            h0v[4 * q + 2] = hh.z + hl.z; h0v[4 * q + 3] = hh.w + hl.w;
+        }
+        if (has_next) stage_slice(na, nh);
         // epilogue 2: gates and the hidden slice; attention projection / score partials
         {
-            const int c0 = 16 * cq;
             float vr[16], vz[16], vi[16], vh[16], hn[16];
             tmem_ld16(t_lane + D + c0, vr);
             tmem_ld16(t_lane + 2 * D + c0, vz);
@@ -316,13 +366,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
             if (HAS_H0) tmem_ld16(t_lane + 4 * D + c0, vh);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float h0v[4] = {0.f, 0.f, 0.f, 0.f};
-                if (HAS_H0) {
-                    const float4 hh = *reinterpret_cast<const float4 *>(smem + L::H_HI + L::off(trow, c0 / 4 + q));
-                    const float4 hl = *reinterpret_cast<const float4 *>(smem + L::H_LO + L::off(trow, c0 / 4 + q));
-                    h0v[0] = hh.x + hl.x; h0v[1] = hh.y + hl.y; h0v[2] = hh.z + hl.z; h0v[3] = hh.w + hl.w;
-                }
-                float sv[5][4];  // r, z, n, W_hn h0 + b_hn, h0 of these 4 columns (training only)
+                float sv[4][4];  // r, z, n, W_hn h0 + b_hn of these 4 columns (training only)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = 4 * q + e, c = c0 + j;
@@ -330,15 +374,17 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                     const float zg = sigmoid_tc(vz[j] + bias[D + c]);
                     const float hlin = (HAS_H0 ? vh[j] : 0.f) + bias[3 * D + c];
                     const float ng = tanh_tc(vi[j] + bias[2 * D + c] + rg * hlin);
-                    hn[j] = (1.0f - zg) * ng + zg * h0v[e];
-                    sv[0][e] = rg; sv[1][e] = zg; sv[2][e] = ng; sv[3][e] = hlin; sv[4][e] = h0v[e];
+                    hn[j] = (1.0f - zg) * ng + zg * h0v[j];
+                    sv[0][e] = rg; sv[1][e] = zg; sv[2][e] = ng; sv[3][e] = hlin;
                 }
                 if (saved && live) {  // planes 1..5 of saved[6][n][D], 128-bit stores
                     const size_t plane = (size_t)n_nodes_host * D, o = (size_t)row * D + c0 + 4 * q;
 #pragma unroll
-                    for (int pl = 0; pl < 5; ++pl)
+                    for (int pl = 0; pl < 4; ++pl)
                         *reinterpret_cast<float4 *>(saved + (pl + 1) * plane + o) =
                             make_float4(sv[pl][0], sv[pl][1], sv[pl][2], sv[pl][3]);
+                    *reinterpret_cast<float4 *>(saved + 5 * plane + o) =
+                        make_float4(h0v[4 * q], h0v[4 * q + 1], h0v[4 * q + 2], h0v[4 * q + 3]);
                 }
             }
             if (live) {
@@ -347,9 +393,12 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                 for (int q = 0; q < 4; ++q) po[q] = make_float4(hn[4 * q], hn[4 * q + 1], hn[4 * q + 2], hn[4 * q + 3]);
             }
             if (as8 || score) {
-                // partial dot products over this thread's 16 columns -> shared memory (the x tile is
-                // free: GEMM 2 has completed), summed in slice order by the cq == 0 thread of the row
-                float *part = reinterpret_cast<float *>(smem + L::A_HI) + ((size_t)cq * kTcRows + trow) * 12;
+                // partial dot products over this thread's 16 columns, exchanged through spare TMEM columns
+                // [5D + 16 cq, +16) of the row's lane (the operand tiles already hold the next tile) and
+                // summed in slice order by the cq == 0 thread of the row
+                float part[16];
+#pragma unroll
+                for (int a = 0; a < 16; ++a) part[a] = 0.f;
 #pragma unroll
                 for (int a = 0; a < 9; ++a) {
                     float sacc = 0.f;
@@ -357,26 +406,32 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                     for (int j = 0; j < 16; ++j) sacc = fmaf(hn[j], ws[a * D + c0 + j], sacc);
                     part[a] = sacc;
                 }
+                if (cq != 0) tmem_st16(t_lane + 5 * D + c0, part);
+                tc_fence_before();
                 __syncthreads();
-                if (cq == 0 && live) {
-                    float proj[9];
+                tc_fence_after();
+                if (cq == 0) {
 #pragma unroll
-                    for (int a = 0; a < 9; ++a) {
-                        float sacc = 0.f;
-                        for (int k = 0; k < D / 16; ++k)
-                            sacc += reinterpret_cast<const float *>(smem + L::A_HI)[((size_t)k * kTcRows + trow) * 12 + a];
-                        proj[a] = sacc;
+                    for (int k = 1; k < D / 16; ++k) {
+                        float other[16];
+                        tmem_ld16(t_lane + 5 * D + 16 * k, other);
+#pragma unroll
+                        for (int a = 0; a < 9; ++a) part[a] += other[a];
                     }
-                    if (as8) {
-                        float4 *po = reinterpret_cast<float4 *>(as8 + (size_t)row * 8);
-                        po[0] = make_float4(proj[0], proj[1], proj[2], proj[3]);
-                        po[1] = make_float4(proj[4], proj[5], proj[6], proj[7]);
+                    if (live) {
+                        if (as8) {
+                            float4 *po = reinterpret_cast<float4 *>(as8 + (size_t)row * 8);
+                            po[0] = make_float4(part[0], part[1], part[2], part[3]);
+                            po[1] = make_float4(part[4], part[5], part[6], part[7]);
+                        }
+                        if (score) score[row] = part[8];
                     }
-                    if (score) score[row] = proj[8];
                 }
             }
         }
-        // TMEM reads and shared-memory reads of this tile are done before the next tile overwrites them
+        // TMEM reads of this tile are done and the staged rows of the next tile are visible to the
+        // async proxy before the next GEMM 1 is issued
+        fence_proxy_async();
         tc_fence_before();
         __syncthreads();
     }
