@@ -350,26 +350,38 @@ def main():
         edges_total += sum(model.last_stats["edges"])
     barrier()
     timing, _lib.Stats.timing = _lib.Stats.timing, None
+    # every step issues the same launches in the same order: per launch slot take the MEDIAN over the
+    # steps (one-off stalls of hundreds of ms were seen right after the nvidia-smi poller exits), then add
+    # the slots up -> milliseconds and algorithmic bytes of one step
     edge_ms, edge_bytes, bwd_ms, bwd_bytes = 0.0, 0.0, 0.0, 0.0
     kernel_ms = {}
-    for name, meta, a, b in timing:
-        kernel_ms[name] = kernel_ms.get(name, 0.0) + a.elapsed_time(b) / args.steps
+    per_step = len(timing) // max(1, args.steps)
+    med = lambda xs: float(np.median(xs))
+    for j in range(per_step):
+        slot = [timing[st * per_step + j] for st in range(args.steps)]
+        name = slot[0][0]
+        ms = med([a.elapsed_time(b) for _, _, a, b in slot])
+        kernel_ms[name] = kernel_ms.get(name, 0.0) + ms
+        if os.environ.get("RG_BENCH_DEBUG"):
+            print("timing", name, [round(a.elapsed_time(b), 3) for _, _, a, b in slot], file=sys.stderr)
         if name == "edge_bwd":
             # push backward over the CSR-by-head: 16 B of structure per edge, the g_agg row of the tail node
             # per edge (4d), the hidden row of the head segment once per segment plus the g_hidden row written
             # (8d per head node, layers >= 1); alpha is recomputed, not stored
-            seg, d, has_hidden = meta
-            n_seg, e_l = seg.n_seg, seg.n_edges or 0
-            bwd_ms += a.elapsed_time(b)
-            bwd_bytes += (16 + 4 * d) * e_l + (8 * d if has_hidden else 0) * n_seg
-        if name != "edge_fwd":
-            continue
-        seg, d, has_hidden = meta
-        fr = getattr(seg, "frontier", None)          # sync-free path: counts resolved by model.last_stats
-        n_seg, e_l = (fr.n_nodes, fr.n_edges) if fr is not None else (seg.n_seg, seg.n_edges)
-        edge_ms += a.elapsed_time(b)
-        edge_bytes += ((16 + 4 * d) if has_hidden else 16) * e_l + 4 * d * n_seg
-    t_instr = edge_ms * 1e-3
+            nbytes = []
+            for _, (seg, d, has_hidden), _, _ in slot:
+                nbytes.append((16 + 4 * d) * (seg.n_edges or 0) + (8 * d if has_hidden else 0) * seg.n_seg)
+            bwd_ms += ms
+            bwd_bytes += med(nbytes)
+        if name == "edge_fwd":
+            nbytes = []
+            for _, (seg, d, has_hidden), _, _ in slot:
+                fr = getattr(seg, "frontier", None)      # sync-free path: counts resolved by model.last_stats
+                n_seg, e_l = (fr.n_nodes, fr.n_edges) if fr is not None else (seg.n_seg, seg.n_edges)
+                nbytes.append(((16 + 4 * d) if has_hidden else 16) * e_l + 4 * d * n_seg)
+            edge_ms += ms
+            edge_bytes += med(nbytes)
+    t_instr = edge_ms * 1e-3 * args.steps          # same units as t_dev (all timed steps)
 
     # subsystem (1): the drop-in get_neighbors chain (explicit sampled_edges / tail_nodes / remap emission,
     # reference load_data.py:106-131) over the first timed batch, device time per hop between CUDA events
@@ -480,10 +492,10 @@ def main():
                        "ms": exp_ms, "ms_emit_part": exp_emit_ms, "edges": exp_edges, "achieved": gbps(exp_bytes, exp_ms), "peak": peak,
                        "unit": "GB/s", "frac": gbps(exp_bytes, exp_ms) / peak,
                        "bytes_model": "56*E + 4*n_fact + 24*N + 16*N' per hop"},
-            "edge_fwd": {"ms_per_step": edge_ms / args.steps, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "edge_fwd": {"ms_per_step": edge_ms, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak},
             "edge_bwd": None if not args.train else {
-                "ms_per_step": bwd_ms / args.steps, "achieved": gbps(bwd_bytes, bwd_ms), "peak": peak,
+                "ms_per_step": bwd_ms, "achieved": gbps(bwd_bytes, bwd_ms), "peak": peak,
                 "unit": "GB/s", "frac": gbps(bwd_bytes, bwd_ms) / peak,
                 "bytes_model": "(16+4d)*E + 8d*N per launch (16+4d)*E at layer 0"},
         },

@@ -206,15 +206,157 @@ __device__ __forceinline__ void store_row(float *dst, const float4 (&acc)[D / 16
     }
 }
 
-template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+// ------------------------------------------------------------------------------------------
+// forward, short segments: the 8 four-lane groups of a warp own 8 consecutive segments and walk
+// their slots one by one (no ballot, no cross-group reduction): a power-law graph's median segment
+// has a handful of slots, and a whole warp per segment would leave 7 of 8 groups idle.  Segments
+// longer than kShortSeg slots are left to the warp-wide fwd_range.  The per-segment sum is again a
+// fixed function of the slot order.  Used by the non-persistent kernel (relation tables too large
+// for shared memory, small layers, explicit segments); measured on the 1M-entity power-law KG:
+// 21.3 -> 15.0 ms per forward.  Inside the 64-register persistent kernel it costs more than it saves
+// (FB15k-237 / YAGO shapes: +9 %), so that kernel keeps one segment per warp.
+// ------------------------------------------------------------------------------------------
+#ifndef RG_SHORT_SEG
+#define RG_SHORT_SEG 12
+#endif
+constexpr int kShortSeg = RG_SHORT_SEG;
+
+template <int D, bool HAS_HIDDEN, bool IMPLICIT, bool SMEM_TAB>
+__device__ __forceinline__ void fwd_group(const rg_segments &S, bool mine, int q, int lo, int len,
+                                          const float *__restrict__ hidden, const float *__restrict__ as8,
+                                          const float *__restrict__ rela, const float *__restrict__ ar8,
+                                          const float *__restrict__ aq8, const float *__restrict__ w8, float b_alpha,
+                                          float4 (&acc)[D / 16], const float *s_rela, const float *s_ar8) {
+    constexpr int NV = D / 16;
+    const int ql = threadIdx.x & 3;
+    const float2 w2 = __ldg(reinterpret_cast<const float2 *>(w8) + ql);
+    float2 aq2 = make_float2(0.f, 0.f);
+    const uint2 *drow = nullptr;
+    int cbase = -1;
+    if (mine) {
+        aq2 = __ldg(reinterpret_cast<const float2 *>(aq8 + (size_t)q * 8) + ql);
+        if (IMPLICIT) {
+            drow = reinterpret_cast<const uint2 *>(S.peer_dict) + (size_t)q * rg_words_ent(S.n_ent);
+            cbase = complete_base_of<IMPLICIT>(S, q);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int max_len = mine ? len : 0;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) max_len = max(max_len, __shfl_xor_sync(RG_FULL_MASK, max_len, o));
+    for (int i = 0; i < max_len; ++i) {
+        const bool valid = mine && i < len;
+        Slot sl = probe_slot<IMPLICIT>(S, drow, cbase, lo + i, valid);
+        const bool on = sl.active;
+        float4 x[NV];
+        float part = 0.f;
+        if (on) {
+            const int p = sl.peer, r = sl.rel;
+            const float4 *rp = SMEM_TAB ? reinterpret_cast<const float4 *>(s_rela + r * D)
+                                        : reinterpret_cast<const float4 *>(rela + (size_t)r * D);
+            float2 z = SMEM_TAB ? reinterpret_cast<const float2 *>(s_ar8 + r * 8)[ql]
+                                : __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
+            if (HAS_HIDDEN) {
+                const float4 *hp = reinterpret_cast<const float4 *>(hidden + (size_t)p * D);
+                float4 h[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) h[v] = ldg4(hp + v * 4 + ql);
+                float2 a = __ldg(reinterpret_cast<const float2 *>(as8 + (size_t)p * 8) + ql);
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    float4 t = SMEM_TAB ? rp[v * 4 + ql] : ldg4(rp + v * 4 + ql);
+                    x[v] = make_float4(h[v].x + t.x, h[v].y + t.y, h[v].z + t.z, h[v].w + t.w);
+                }
+                z.x += a.x;
+                z.y += a.y;
+            } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) x[v] = SMEM_TAB ? rp[v * 4 + ql] : ldg4(rp + v * 4 + ql);
+            }
+            z.x += aq2.x;
+            z.y += aq2.y;
+            part = w2.x * fmaxf(z.x, 0.f) + w2.y * fmaxf(z.y, 0.f);
+        } else {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) x[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        part += __shfl_xor_sync(RG_FULL_MASK, part, 1);
+        part += __shfl_xor_sync(RG_FULL_MASK, part, 2);
+        const float alpha = on ? sigmoidf_(part + b_alpha) : 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            acc[v].x = fmaf(alpha, x[v].x, acc[v].x);
+            acc[v].y = fmaf(alpha, x[v].y, acc[v].y);
+            acc[v].z = fmaf(alpha, x[v].z, acc[v].z);
+            acc[v].w = fmaf(alpha, x[v].w, acc[v].w);
+        }
+    }
+}
+
+// one warp, 8 consecutive segments starting at seg0: short ones group-wise, then the long ones warp-wide
+template <int D, bool HAS_HIDDEN, bool IMPLICIT, bool SMEM_TAB>
+__device__ __forceinline__ void fwd_block8(const rg_segments &S, int64_t seg0, int64_t n_true,
+                                           const float *__restrict__ hidden, const float *__restrict__ as8,
+                                           const float *__restrict__ rela, const float *__restrict__ ar8,
+                                           const float *__restrict__ aq8, const float *__restrict__ w8, float b_alpha,
+                                           float *__restrict__ agg, const rg_heavy &H, int has_heavy,
+                                           const float *s_rela, const float *s_ar8) {
+    const int lane = threadIdx.x & 31, grp = lane >> 2, ql = lane & 3;
+    const int64_t seg = seg0 + grp;
+    const bool valid = seg < n_true;
+    SegRange r;
+    r.q = 0;
+    r.lo = 0;
+    r.hi = 0;
+    if (valid) r = seg_range<IMPLICIT>(S, seg);
+    const int len = r.hi - r.lo;
+    const bool is_short = valid && len <= kShortSeg;
+    float4 acc[D / 16];
+    if (__any_sync(RG_FULL_MASK, is_short)) {
+        fwd_group<D, HAS_HIDDEN, IMPLICIT, SMEM_TAB>(S, is_short, r.q, r.lo, len, hidden, as8, rela, ar8, aq8, w8,
+                                                     b_alpha, acc, s_rela, s_ar8);
+        if (is_short) {
+            float4 *o = reinterpret_cast<float4 *>(agg + (size_t)seg * D);
+#pragma unroll
+            for (int v = 0; v < D / 16; ++v) o[v * 4 + ql] = acc[v];
+        }
+    }
+    unsigned long_mask = __ballot_sync(RG_FULL_MASK, valid && !is_short && ql == 0);
+    while (long_mask) {  // warp-uniform
+        const int src = __ffs(long_mask) - 1;
+        long_mask &= long_mask - 1;
+        const int q = __shfl_sync(RG_FULL_MASK, r.q, src);
+        const int lo = __shfl_sync(RG_FULL_MASK, r.lo, src);
+        int hi = __shfl_sync(RG_FULL_MASK, r.hi, src);
+        const int64_t sg = seg0 + (src >> 2);
+        if (has_heavy && hi - lo > RG_HEAVY_CHUNK) {
+            enqueue_heavy(H, sg, hi - lo, lane);
+            hi = lo + RG_HEAVY_CHUNK;
+        }
+        fwd_range<D, HAS_HIDDEN, IMPLICIT, SMEM_TAB>(S, q, lo, hi, hidden, as8, rela, ar8, aq8, w8, b_alpha, acc,
+                                                     s_rela, s_ar8);
+        store_row<D>(agg + (size_t)sg * D, acc, lane);
+    }
+}
+
+template <int D, bool HAS_HIDDEN, bool IMPLICIT, bool BLOCK8>
 __global__ void __launch_bounds__(kBlock, 5) k_edge_fwd(rg_segments S, const float *__restrict__ hidden,
                                                      const float *__restrict__ as8, const float *__restrict__ rela,
                                                      const float *__restrict__ ar8, const float *__restrict__ aq8,
                                                      const float *__restrict__ w8, const float *__restrict__ b_alpha,
                                                      float *__restrict__ agg, rg_heavy H, int has_heavy) {
+    const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
+    if (BLOCK8) {  // many segments: 8 per warp, the short ones group-wise
+        const int64_t seg0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * 8;
+        if (seg0 >= n_true) return;
+        fwd_block8<D, HAS_HIDDEN, IMPLICIT, false>(S, seg0, n_true, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), agg,
+                                                   H, has_heavy, nullptr, nullptr);
+        return;
+    }
     const int lane = threadIdx.x & 31;
     const int64_t seg = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (seg >= (S.n_seg_dev ? *S.n_seg_dev : S.n_seg)) return;
+    if (seg >= n_true) return;
     SegRange r = seg_range<IMPLICIT>(S, seg);
     int hi = r.hi;
     if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all
@@ -473,6 +615,99 @@ __device__ __forceinline__ void bwd_range(const rg_segments &S, int64_t seg, int
     }
 }
 
+// backward, short segments: same group-per-segment scheme as fwd_group (see there)
+template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+__device__ __forceinline__ void bwd_group(const rg_segments &S, bool mine, int64_t seg, int q, int lo, int len,
+                                          const float *__restrict__ hidden, const float *__restrict__ as8,
+                                          const float *__restrict__ rela, const float *__restrict__ ar8,
+                                          const float *__restrict__ aq8, const float *__restrict__ w8, float b_alpha,
+                                          const float *__restrict__ g_agg, float *g_rela, float *g_ar8,
+                                          float4 (&G)[D / 16], BwdSmall &sm) {
+    constexpr int NV = D / 16;
+    const int ql = threadIdx.x & 3;
+    const float2 w2 = __ldg(reinterpret_cast<const float2 *>(w8) + ql);
+    float2 zbase = make_float2(0.f, 0.f);
+    float4 hs[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) hs[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint2 *drow = nullptr;
+    int cbase = -1;
+    if (mine) {
+        zbase = __ldg(reinterpret_cast<const float2 *>(aq8 + (size_t)q * 8) + ql);
+        if (HAS_HIDDEN) {
+            const float4 *hp = reinterpret_cast<const float4 *>(hidden + (size_t)seg * D);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) hs[v] = ldg4(hp + v * 4 + ql);
+            float2 a = __ldg(reinterpret_cast<const float2 *>(as8 + (size_t)seg * 8) + ql);
+            zbase.x += a.x;
+            zbase.y += a.y;
+        }
+        if (IMPLICIT) {
+            drow = reinterpret_cast<const uint2 *>(S.peer_dict) + (size_t)q * rg_words_ent(S.n_ent);
+            cbase = complete_base_of<IMPLICIT>(S, q);
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) G[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sm.z = make_float2(0.f, 0.f);
+    sm.wz = make_float2(0.f, 0.f);
+    sm.gl = 0.f;
+    int max_len = mine ? len : 0;
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) max_len = max(max_len, __shfl_xor_sync(RG_FULL_MASK, max_len, o));
+    for (int i = 0; i < max_len; ++i) {
+        Slot sl = probe_slot<IMPLICIT>(S, drow, cbase, lo + i, mine && i < len);
+        const bool on = sl.active;
+        const int r = sl.rel;
+        float4 g[NV];
+        float2 z = zbase;
+        float dot = 0.f, part = 0.f;
+        if (on) {
+            const float4 *gp = reinterpret_cast<const float4 *>(g_agg + (size_t)sl.peer * D);
+            const float4 *rp = reinterpret_cast<const float4 *>(rela + (size_t)r * D);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) g[v] = ldg4(gp + v * 4 + ql);
+            float2 a = __ldg(reinterpret_cast<const float2 *>(ar8 + (size_t)r * 8) + ql);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                float4 t = ldg4(rp + v * 4 + ql);
+                dot = fmaf(g[v].x, hs[v].x + t.x, dot);
+                dot = fmaf(g[v].y, hs[v].y + t.y, dot);
+                dot = fmaf(g[v].z, hs[v].z + t.z, dot);
+                dot = fmaf(g[v].w, hs[v].w + t.w, dot);
+            }
+            z.x += a.x;
+            z.y += a.y;
+            part = w2.x * fmaxf(z.x, 0.f) + w2.y * fmaxf(z.y, 0.f);
+        }
+        part += __shfl_xor_sync(RG_FULL_MASK, part, 1);
+        part += __shfl_xor_sync(RG_FULL_MASK, part, 2);
+        dot += __shfl_xor_sync(RG_FULL_MASK, dot, 1);
+        dot += __shfl_xor_sync(RG_FULL_MASK, dot, 2);
+        if (on) {
+            const float alpha = sigmoidf_(part + b_alpha);
+            const float gl = dot * alpha * (1.f - alpha);
+            float2 gz = make_float2(z.x > 0.f ? gl * w2.x : 0.f, z.y > 0.f ? gl * w2.y : 0.f);
+            sm.z.x += gz.x;
+            sm.z.y += gz.y;
+            sm.wz.x = fmaf(gl, fmaxf(z.x, 0.f), sm.wz.x);
+            sm.wz.y = fmaf(gl, fmaxf(z.y, 0.f), sm.wz.y);
+            sm.gl += gl;
+            float4 *gr = reinterpret_cast<float4 *>(g_rela + (size_t)r * D);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                float4 ag = make_float4(alpha * g[v].x, alpha * g[v].y, alpha * g[v].z, alpha * g[v].w);
+                G[v].x += ag.x;
+                G[v].y += ag.y;
+                G[v].z += ag.z;
+                G[v].w += ag.w;
+                atomicAdd(gr + v * 4 + ql, ag);
+            }
+            atomicAdd(reinterpret_cast<float2 *>(g_ar8 + (size_t)r * 8) + ql, gz);
+        }
+    }
+}
+
 // The relation-gradient accumulators may be replicated (`copies` > 1, [copies][rows][D] and
 // [copies][rows][8]): a CTA adds into copy blockIdx % copies, which spreads the fp32 reductions of
 // the few thousand hot sectors over `copies` times as many L2 lines; the caller sums the copies.
@@ -495,7 +730,7 @@ __device__ __forceinline__ void store_small(float *dst, const BwdSmall &sm, int 
     }
 }
 
-template <int D, bool HAS_HIDDEN, bool IMPLICIT>
+template <int D, bool HAS_HIDDEN, bool IMPLICIT, bool BLOCK8>
 __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float *__restrict__ hidden,
                                                      const float *__restrict__ as8, const float *__restrict__ rela,
                                                      const float *__restrict__ ar8, const float *__restrict__ aq8,
@@ -505,20 +740,71 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
                                                      rg_heavy H, int has_heavy) {
     const int lane = threadIdx.x & 31;
     select_copy<D>(g_rela, g_ar8, copies, S.n_table_rows);
-    const int64_t seg = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (seg >= (S.n_seg_dev ? *S.n_seg_dev : S.n_seg)) return;
-    SegRange r = seg_range<IMPLICIT>(S, seg);
-    int hi = r.hi;
-    if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all
-        enqueue_heavy(H, seg, r.hi - r.lo, lane);
-        hi = r.lo + RG_HEAVY_CHUNK;
+    const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
+    const float ba = __ldg(b_alpha);
+    if (!BLOCK8) {  // one warp per segment
+        const int64_t seg = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+        if (seg >= n_true) return;
+        SegRange r = seg_range<IMPLICIT>(S, seg);
+        int hi = r.hi;
+        if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all
+            enqueue_heavy(H, seg, r.hi - r.lo, lane);
+            hi = r.lo + RG_HEAVY_CHUNK;
+        }
+        float4 G[D / 16];
+        BwdSmall sm;
+        bwd_range<D, HAS_HIDDEN, IMPLICIT>(S, seg, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, g_agg, g_rela,
+                                           g_ar8, G, sm);
+        if (g_hidden) store_row<D>(g_hidden + (size_t)seg * D, G, lane);
+        store_small(node_small + (size_t)seg * 24, sm, lane);
+        return;
     }
+    const int grp = lane >> 2, ql = lane & 3;
+    const int64_t seg0 = ((int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5)) * 8;
+    if (seg0 >= n_true) return;
+    const int64_t seg = seg0 + grp;
+    const bool valid = seg < n_true;
+    SegRange r;
+    r.q = 0;
+    r.lo = 0;
+    r.hi = 0;
+    if (valid) r = seg_range<IMPLICIT>(S, seg);
+    const int len = r.hi - r.lo;
+    const bool is_short = valid && len <= kShortSeg;
     float4 G[D / 16];
     BwdSmall sm;
-    bwd_range<D, HAS_HIDDEN, IMPLICIT>(S, seg, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), g_agg,
-                                       g_rela, g_ar8, G, sm);
-    if (g_hidden) store_row<D>(g_hidden + (size_t)seg * D, G, lane);
-    store_small(node_small + (size_t)seg * 24, sm, lane);
+    if (__any_sync(RG_FULL_MASK, is_short)) {  // short segments: one per 4-lane group
+        bwd_group<D, HAS_HIDDEN, IMPLICIT>(S, is_short, seg, r.q, r.lo, len, hidden, as8, rela, ar8, aq8, w8, ba, g_agg,
+                                           g_rela, g_ar8, G, sm);
+        if (is_short) {
+            if (g_hidden) {
+                float4 *o = reinterpret_cast<float4 *>(g_hidden + (size_t)seg * D);
+#pragma unroll
+                for (int v = 0; v < D / 16; ++v) o[v * 4 + ql] = G[v];
+            }
+            float2 *o = reinterpret_cast<float2 *>(node_small + (size_t)seg * 24);
+            o[ql] = sm.z;
+            o[4 + ql] = sm.wz;
+            o[8 + ql] = make_float2(ql == 0 ? sm.gl : 0.f, 0.f);
+        }
+    }
+    unsigned long_mask = __ballot_sync(RG_FULL_MASK, valid && !is_short && ql == 0);
+    while (long_mask) {  // the long ones, warp-wide, one after the other (warp-uniform loop)
+        const int src = __ffs(long_mask) - 1;
+        long_mask &= long_mask - 1;
+        const int q = __shfl_sync(RG_FULL_MASK, r.q, src);
+        const int lo = __shfl_sync(RG_FULL_MASK, r.lo, src);
+        int hi = __shfl_sync(RG_FULL_MASK, r.hi, src);
+        const int64_t sg = seg0 + (src >> 2);
+        if (has_heavy && hi - lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all
+            enqueue_heavy(H, sg, hi - lo, lane);
+            hi = lo + RG_HEAVY_CHUNK;
+        }
+        bwd_range<D, HAS_HIDDEN, IMPLICIT>(S, sg, q, lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, g_agg, g_rela, g_ar8,
+                                           G, sm);
+        if (g_hidden) store_row<D>(g_hidden + (size_t)sg * D, G, lane);
+        store_small(node_small + (size_t)sg * 24, sm, lane);
+    }
 }
 
 // Persistent variant (implicit path): warps loop over segments on their own, so a block never idles
@@ -612,6 +898,8 @@ int check_heavy(const rg_heavy *h) {
 }
 
 constexpr int kHeavyGrid = 148 * 4;
+// 8 segments per warp only pays when that still leaves every SM several blocks of warps
+constexpr int64_t kBlock8MinSegs = 8 * 148 * 64;
 
 template <int D, bool HH, bool IM>
 int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, const float *rela, const float *ar8,
@@ -643,9 +931,15 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
         }
     }
     if (!persistent) {
-        const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
-        k_edge_fwd<D, HH, IM><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, agg, H,
-                                                       has_heavy);
+        if (seg->n_seg >= kBlock8MinSegs) {
+            const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock * 8);
+            k_edge_fwd<D, HH, IM, true><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, agg, H,
+                                                                 has_heavy);
+        } else {
+            const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
+            k_edge_fwd<D, HH, IM, false><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, agg, H,
+                                                                  has_heavy);
+        }
         RG_LAUNCH_CHECK();
     }
     if (has_heavy) {
@@ -686,9 +980,17 @@ int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, co
         }
     }
     if (!persistent) {
-        const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
-        k_edge_bwd<D, HH, IM><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, g_hidden,
-                                                       node_small, g_rela, g_ar8, copies, H, has_heavy);
+        if (seg->n_seg >= kBlock8MinSegs) {
+            const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock * 8);
+            k_edge_bwd<D, HH, IM, true><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,
+                                                                 g_hidden, node_small, g_rela, g_ar8, copies, H,
+                                                                 has_heavy);
+        } else {
+            const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
+            k_edge_bwd<D, HH, IM, false><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,
+                                                                  g_hidden, node_small, g_rela, g_ar8, copies, H,
+                                                                  has_heavy);
+        }
         RG_LAUNCH_CHECK();
     }
     if (has_heavy) {

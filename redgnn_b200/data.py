@@ -65,6 +65,16 @@ def _multi_hot(answers, batch_idx, n_ent):
     return objs
 
 
+def _cached_query_array(obj, name):
+    """np.array(self.valid_q) per call (load_data.py:139-146) converts the whole list every batch;
+    the list never changes after __init__, so the array is built once."""
+    cache = obj.__dict__.setdefault('_q_arrays', {})
+    arr = cache.get(name)
+    if arr is None:
+        arr = cache[name] = np.array(getattr(obj, name))
+    return arr
+
+
 class _GraphSlot(object):
     """Host triples of one KG + its lazily built device copy."""
 
@@ -166,14 +176,17 @@ class TransductiveLoader(object):
 
     def get_batch(self, batch_idx, steps=2, data='train'):
         if data == 'train':
-            return np.array(self.train_data)[batch_idx]
+            return np.asarray(self.train_data)[batch_idx]      # fancy indexing copies the batch only
         if data == 'valid':
-            query, answer = np.array(self.valid_q), self.valid_a
+            query, answer = self._query_array('valid_q'), self.valid_a
         if data == 'test':
-            query, answer = np.array(self.test_q), self.test_a
+            query, answer = self._query_array('test_q'), self.test_a
         subs = query[batch_idx, 0]
         rels = query[batch_idx, 1]
         return subs, rels, _multi_hot(answer, batch_idx, self.n_ent)
+
+    def _query_array(self, name):
+        return _cached_query_array(self, name)
 
     def shuffle_train(self):
         """load_data.py:152-164: re-split facts+train 3:1 with np.random and rebuild the graph."""
@@ -269,12 +282,15 @@ class InductiveLoader(object):
         if data == 'train':
             return self.tra_train[batch_idx]
         if data == 'valid':
-            query, answer, n_ent = np.array(self.valid_q), self.valid_a, self.n_ent
+            query, answer, n_ent = self._query_array('valid_q'), self.valid_a, self.n_ent
         if data == 'test':
-            query, answer, n_ent = np.array(self.test_q), self.test_a, self.n_ent_ind
+            query, answer, n_ent = self._query_array('test_q'), self.test_a, self.n_ent_ind
         subs = query[batch_idx, 0]
         rels = query[batch_idx, 1]
         return subs, rels, _multi_hot(answer, batch_idx, n_ent)
+
+    def _query_array(self, name):
+        return _cached_query_array(self, name)
 
     def shuffle_train(self):
         rand_idx = np.random.permutation(self.n_train)

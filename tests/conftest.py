@@ -27,6 +27,16 @@ def hub_dir(tmp_path_factory):
 
 
 @pytest.fixture(scope="session")
+def manyrel_dir(tmp_path_factory):
+    """KG with 300 relations (601 table rows: too large for the shared-memory relation tables) and a
+    power-law degree distribution: with >= 32 queries the edge kernels take the non-persistent
+    8-segments-per-warp path (short segments per 4-lane group)."""
+    from redgnn_b200 import synth
+    return synth.write_transductive(str(tmp_path_factory.mktemp("manyrel")), seed=7,
+                                    override=(3000, 300, 24000, 100, 100, 1.0, 1.0, 3))
+
+
+@pytest.fixture(scope="session")
 def induc_dir(tmp_path_factory):
     from redgnn_b200 import synth
     return synth.write_inductive(os.path.join(str(tmp_path_factory.mktemp("induc")), "syn_v1"), seed=11)

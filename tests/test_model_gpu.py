@@ -125,6 +125,32 @@ def test_hub_model_vs_oracle(hub_dir):
         assert_grad_close(p.grad, g32[k], g64[k], 1e-4, "hub grad " + k, floor=grad_floor(g64))
 
 
+def test_many_relations_short_segment_path_vs_oracle(manyrel_dir):
+    """601 relation-table rows and 32 x 3000 >= 75,776 (upper-bound) segments: forward / backward run the
+    non-persistent kernels with 8 segments per warp (rg_edge.cu: fwd_block8 / bwd_group)."""
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    L, D = TransductiveLoader(manyrel_dir), O.TransductiveData(manyrel_dir)
+    sd = O.init_state_dict(3, 48, 5, D.n_rel, seed=13)
+    model = RED_GNN_trans(Options(n_rel=L.n_rel), L).cuda()
+    model.load_state_dict(sd)
+    model.eval()
+    subs, rels, _ = L.get_batch(np.arange(32), data="valid")
+    got = model(subs, rels, mode="valid")
+    want = O.model_forward(sd, D.test_graph, subs, rels, 3, "relu")
+    assert_close(got, want, 1e-4, "many-relation scores")
+    assert torch.equal(got, model(subs, rels, mode="valid"))
+    model.train()
+    tri = L.get_batch(np.arange(32))
+    g32, g64 = oracle_loss_grads(sd, D.graph, tri, 3, "relu")
+    for graph_train in (True, False):           # captured training step, then the eager autograd path
+        model.graph_train = graph_train
+        model.zero_grad(set_to_none=True)
+        cuda_loss_backward(model, tri)
+        for k, p in model.named_parameters():
+            assert_grad_close(p.grad, g32[k], g64[k], 1e-4, "many-relation grad %s (graph=%s)" % (k, graph_train),
+                              floor=grad_floor(g64))
+
+
 def test_inductive_model_vs_oracle_and_golden(induc_dir):
     from redgnn_b200 import InductiveLoader, RED_GNN_induc
     L, D = InductiveLoader(induc_dir), O.InductiveData(induc_dir)
