@@ -43,12 +43,15 @@ def _read_raw_triples(path, ent, rel):
 
 
 def _group_queries(triples):
-    """load_query (transductive/load_data.py:91-104): queries keyed by (h, r) in sorted order."""
-    triples.sort(key=lambda x: (x[0], x[1]))
-    table = defaultdict(list)
-    for h, r, t in triples:
-        table[(h, r)].append(t)
-    return list(table.keys()), [np.array(v) for v in table.values()]
+    """load_query (transductive/load_data.py:91-104): queries keyed by (h, r) in sorted order, the
+    answers of a query in file order (the reference's list.sort is stable; so is lexsort)."""
+    a = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+    if len(a) == 0:
+        return [], []
+    a = a[np.lexsort((a[:, 1], a[:, 0]))]
+    starts = np.flatnonzero(np.r_[True, (a[1:, 0] != a[:-1, 0]) | (a[1:, 1] != a[:-1, 1])])
+    keys = [(int(h), int(r)) for h, r in a[starts, :2]]
+    return keys, np.split(a[:, 2].copy(), starts[1:])
 
 
 def _ragged(lst):
@@ -117,12 +120,12 @@ class TransductiveLoader(object):
         self.test_triple = self.read_triples('test.txt')
 
         self.fact_data = self.double_triple(self.fact_triple)
-        self.train_data = np.array(self.double_triple(self.train_triple))
+        self.train_data = self.double_triple(self.train_triple)
         self.valid_data = self.double_triple(self.valid_triple)
         self.test_data = self.double_triple(self.test_triple)
 
         self.load_graph(self.fact_data)
-        self.load_test_graph(self.double_triple(self.fact_triple) + self.double_triple(self.train_triple))
+        self.load_test_graph(np.concatenate([self.fact_data, self.train_data], axis=0))
 
         self.valid_q, self.valid_a = _group_queries(self.valid_data)
         self.test_q, self.test_a = _group_queries(self.test_data)
@@ -145,8 +148,12 @@ class TransductiveLoader(object):
         return triples
 
     def double_triple(self, triples):
-        """Inverse triples appended as one block after the originals (load_data.py:69-74)."""
-        return list(triples) + [[t, r + self.n_rel, h] for h, r, t in triples]
+        """Inverse triples appended as one block after the originals (load_data.py:69-74).  Returns an
+        int64 array (the reference builds a list of lists row by row; at 10 M facts that loop alone
+        takes minutes per epoch in `shuffle_train`)."""
+        a = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+        inv = np.stack([a[:, 2], a[:, 1] + self.n_rel, a[:, 0]], axis=1)
+        return np.concatenate([a, inv], axis=0)
 
     def load_graph(self, triples):
         self._train_graph = _GraphSlot(triples, self.n_ent, self.n_rel)
@@ -193,8 +200,8 @@ class TransductiveLoader(object):
         all_triple = np.concatenate([np.array(self.fact_triple), np.array(self.train_triple)], axis=0)
         n_all = len(all_triple)
         all_triple = all_triple[np.random.permutation(n_all)]
-        self.fact_data = self.double_triple(all_triple[:n_all * 3 // 4].tolist())
-        self.train_data = np.array(self.double_triple(all_triple[n_all * 3 // 4:].tolist()))
+        self.fact_data = self.double_triple(all_triple[:n_all * 3 // 4])
+        self.train_data = self.double_triple(all_triple[n_all * 3 // 4:])
         self.n_train = len(self.train_data)
         self.load_graph(self.fact_data)
 
