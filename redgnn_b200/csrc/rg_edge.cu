@@ -19,7 +19,9 @@ constexpr int kWarpsPerBlock = 8;
 constexpr int kBlock = kWarpsPerBlock * 32;
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// ex2.approx / rcp.approx form (5 instructions instead of ~28 for the IEEE division + expf; relative
+// error ~2^-21, far inside the 1e-4 parity bound).  Forward and backward use the same function.
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 struct Slot {
     int peer;  // row of the peer node (valid when active)
