@@ -222,8 +222,10 @@ int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_n
                          const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                          const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
                          float *hidden, float *saved, void *stream);
-int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *g_hidden,
-                    const float *saved, float *g_gi, float *g_gh, float *g_h0_direct,
+/* saved_plane_rows: rows per plane of `saved` (0 = n_nodes); lets a caller process only the first
+ * n_nodes <= saved_plane_rows rows of buffers that were written with a larger row capacity. */
+int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_rows, const int64_t *n_nodes_dev,
+                    const float *g_hidden, const float *saved, float *g_gi, float *g_gh, float *g_h0_direct,
                     float *bias_partial /* optional [ceil(n/64)][4][D]: per-CTA column sums of g_r, g_z, g_n, g_n*r */,
                     void *stream);
 

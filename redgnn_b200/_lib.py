@@ -59,7 +59,7 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p]),
     "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 4),
     "rg_node_update_train": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 9 + [C.c_int32] + [C.c_void_p] * 4),
-    "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 8),
+    "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64, C.c_int64] + [C.c_void_p] * 8),
     "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
     "rg_scatter_rows": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
     "rg_query_sum8": (C.c_int, [C.c_int32] + [C.c_void_p] * 4),

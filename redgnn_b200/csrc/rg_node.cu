@@ -362,14 +362,15 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
 constexpr int kGruRows = 64;
 
 template <int D>
-__global__ void __launch_bounds__(4 * D) k_gru_bwd_elem(int64_t n_rows, const int64_t *__restrict__ n_dev,
+__global__ void __launch_bounds__(4 * D) k_gru_bwd_elem(int64_t n_rows, int64_t plane_rows,
+                                                        const int64_t *__restrict__ n_dev,
                                                         const float *__restrict__ g_h,
                                                         const float *__restrict__ saved, float *__restrict__ g_gi,
                                                         float *__restrict__ g_gh, float *__restrict__ g_h0d,
                                                         float *__restrict__ bias_partial) {
     __shared__ float sm[4][4][D];
     const int c = threadIdx.x % D, rl = threadIdx.x / D;  // 4 row lanes
-    const int64_t n_true = n_dev ? *n_dev : n_rows, n_elem = n_rows * D;
+    const int64_t n_true = n_dev ? *n_dev : n_rows, n_elem = plane_rows * D;  // saved[6][plane_rows][D]
     const int64_t row0 = (int64_t)blockIdx.x * kGruRows;
     float s_r = 0.f, s_z = 0.f, s_n = 0.f, s_nr = 0.f;
     for (int k = rl; k < kGruRows; k += 4) {
@@ -414,18 +415,20 @@ __global__ void __launch_bounds__(4 * D) k_gru_bwd_elem(int64_t n_rows, const in
     }
 }
 
-extern "C" int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev,
-                               const float *g_hidden, const float *saved, float *g_gi, float *g_gh,
-                               float *g_h0_direct, float *bias_partial, void *stream) {
+extern "C" int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_rows,
+                               const int64_t *n_nodes_dev, const float *g_hidden, const float *saved, float *g_gi,
+                               float *g_gh, float *g_h0_direct, float *bias_partial, void *stream) {
     if (n_nodes < 0 || hidden_dim <= 0 || !g_hidden || !saved || !g_gi || !g_gh || !g_h0_direct) return RG_ERR_BAD_ARG;
     if (n_nodes == 0) return RG_OK;
     const unsigned grid = (unsigned)rg_cdiv(n_nodes, kGruRows);
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t plane = saved_plane_rows > 0 ? saved_plane_rows : n_nodes;
+    if (plane < n_nodes) return RG_ERR_BAD_ARG;
     switch (hidden_dim) {
-        case 16: k_gru_bwd_elem<16><<<grid, 64, 0, st>>>(n_nodes, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
-        case 32: k_gru_bwd_elem<32><<<grid, 128, 0, st>>>(n_nodes, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
-        case 48: k_gru_bwd_elem<48><<<grid, 192, 0, st>>>(n_nodes, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
-        case 64: k_gru_bwd_elem<64><<<grid, 256, 0, st>>>(n_nodes, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
+        case 16: k_gru_bwd_elem<16><<<grid, 64, 0, st>>>(n_nodes, plane, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
+        case 32: k_gru_bwd_elem<32><<<grid, 128, 0, st>>>(n_nodes, plane, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
+        case 48: k_gru_bwd_elem<48><<<grid, 192, 0, st>>>(n_nodes, plane, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
+        case 64: k_gru_bwd_elem<64><<<grid, 256, 0, st>>>(n_nodes, plane, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
         default: return RG_ERR_UNSUPPORTED;
     }
     RG_LAUNCH_CHECK();

@@ -210,7 +210,7 @@ class NodeUpdateTrain(torch.autograd.Function):
         g_gi = torch.empty((n, 3 * d), dtype=torch.float32, device=agg.device)
         g_gh = torch.empty((n, 3 * d), dtype=torch.float32, device=agg.device)
         g_h0d = torch.empty((n, d), dtype=torch.float32, device=agg.device)
-        check(lib.rg_gru_bwd_elem(d, n, None, ptr(g_h), ptr(saved), ptr(g_gi), ptr(g_gh), ptr(g_h0d), None,
+        check(lib.rg_gru_bwd_elem(d, n, 0, None, ptr(g_h), ptr(saved), ptr(g_gi), ptr(g_gh), ptr(g_h0d), None,
                                   stream_ptr()))
         _lib.Stats.launches += 1
         x_act, h0 = saved[0], saved[5]

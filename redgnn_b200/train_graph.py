@@ -13,8 +13,17 @@ Invariant that makes upper-bound buffers safe: every persistent buffer starts as
 holds finite values, and every gradient row past the true node count is an exact zero
 (rg_gru_bwd_elem / rg_gather_scores write zeros there, node_small is cleared per replay), so stale
 rows only ever meet zeros in the reductions over nodes.
+
+The forward always runs on the full upper-bound buffers.  The backward is dominated by dense GEMMs
+over node rows that cannot stop at a device-side count, and the early layers hold far fewer nodes
+than `n_query * n_ent`; so the backward exists as a few captured variants, one per tuple of
+per-layer row capacities (a geometric ladder of 1024-row multiples).  Before the backward replay the
+true per-layer node counts of the forward are read back (one 8-byte-per-layer copy) and the
+cheapest captured variant that covers them is replayed; tighter variants are captured during the
+first few steps of a runner only (TrainStepRunner.replay_backward).
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn.functional as F
@@ -72,6 +81,16 @@ class TrainStepRunner(object):
         self.L = None
         self.scores = None
         self.version = 0
+        # row-capacity ladder for the backward variants: cap, cap/1.5, ... (multiples of _SPLIT, >= 4 slabs)
+        self.ladder = [self.cap]
+        while self.ladder[-1] > 4 * _SPLIT:
+            nxt = max(4 * _SPLIT, -(-int(self.ladder[-1] / 1.5) // _SPLIT) * _SPLIT)
+            if nxt >= self.ladder[-1]:
+                break
+            self.ladder.append(nxt)
+        self.ladder.reverse()
+        self.bwd_graphs = {}           # caps tuple -> (CUDAGraph, launches)
+        self.bwd_replays = 0
         self._build()
 
     # ------------------------------------------------------------------------------------------
@@ -131,18 +150,22 @@ class TrainStepRunner(object):
         return scores
 
     # ------------------------------------------------------------------------------------------
-    def _backward(self):
-        m, n, d, a, cap, dev = self.model, self.n, self.d, self.a, self.cap, self.dev
+    def _backward(self, caps):
+        """caps[i]: rows processed for layer i's OUTPUT nodes (>= the true count of this step, a
+        multiple of _SPLIT, <= self.cap); layer i's input rows are caps[i-1]."""
+        m, n, d, a, dev = self.model, self.n, self.d, self.a, self.dev
+        full = self.cap
         st = stream_ptr
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
         e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         grads = {}
         last = self.L[-1]
+        cap = caps[-1]
         g_node = e(cap)
         check(lib.rg_gather_scores(cap, ptr(last["n_dev"]), ptr(last["nb"]), ptr(last["ne"]), ptr(self.g_out),
                                    self.n_ent_out, ptr(g_node), st()))
         _lib.Stats.launches += 1
-        grads["W_final.weight"] = _tn(g_node[:, None], self.hidden[-1])
+        grads["W_final.weight"] = _tn(g_node[:, None], self.hidden[-1][:cap])
         g_hidden = g_node[:, None] * m.W_final.weight
         gate = m.gate
         w_ih, w_hh = gate.weight_ih_l0, gate.weight_hh_l0
@@ -151,13 +174,17 @@ class TrainStepRunner(object):
             lay, layer = self.L[i], m.gnn_layers[i]
             pre = "gnn_layers.%d." % i
             saved, mask = self.saved[i], lay["mask"]
+            cap = caps[i]                                    # rows of this layer's output nodes
+            cap_in = caps[i - 1] if i > 0 else n             # rows of its input nodes
+            if mask is not None:
+                mask = mask[:cap]
             g_hidden = g_hidden.contiguous()
             g_gi, g_gh, g_h0d = e(cap, 3 * d), e(cap, 3 * d), e(cap, d)
             bias_part = z(-(-cap // 64), 4, d)               # per-CTA column sums of g_r, g_z, g_n, g_n * r
-            check(lib.rg_gru_bwd_elem(d, cap, ptr(lay["n_dev"]), ptr(g_hidden), ptr(saved), ptr(g_gi), ptr(g_gh),
-                                      ptr(g_h0d), ptr(bias_part), st()))
+            check(lib.rg_gru_bwd_elem(d, cap, full, ptr(lay["n_dev"]), ptr(g_hidden), ptr(saved), ptr(g_gi),
+                                      ptr(g_gh), ptr(g_h0d), ptr(bias_part), st()))
             bsum = bias_part.sum(0)                          # [4, d]
-            x_act = saved[0]
+            x_act = saved[0][:cap]
             x_in = x_act * mask if mask is not None else x_act
             d_wih += _tn(g_gi, x_in)
             d_bih += bsum[:3].reshape(-1)
@@ -169,17 +196,16 @@ class TrainStepRunner(object):
                 g_x = g_x * (x_act > 0)
             elif self.act_code == 2:
                 g_x = g_x * (1.0 - x_act * x_act)
-            grads[pre + "W_h.weight"] = _tn(g_x, self.agg[i])
+            grads[pre + "W_h.weight"] = _tn(g_x, self.agg[i][:cap])
             g_agg = (g_x @ layer.W_h.weight).contiguous()
             hidden_prev, g_h0 = lay["hidden_prev"], None
             if hidden_prev is not None:
-                d_whh += _tn(g_gh, saved[5])
+                d_whh += _tn(g_gh, saved[5][:cap])
                 g_h0 = torch.addmm(g_h0d, g_gh, w_hh)
             # fused edge backward on the same implicit segments (grouped by the layer's INPUT nodes)
             bwd_seg, rela = lay["bwd_seg"], lay["rela"]
-            n_seg = bwd_seg.n_seg
-            node_small = z(n_seg, 24)
-            g_hid_e = z(n_seg, d) if hidden_prev is not None else None
+            node_small = z(cap_in, 24)                       # the kernels stop at the true input-node count
+            g_hid_e = z(cap_in, d) if hidden_prev is not None else None
             copies = _lib.GRAD_COPIES
             g_rela, g_ar8 = z(copies, rela.shape[0], d), z(copies, rela.shape[0], 8)
             heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
@@ -205,7 +231,7 @@ class TrainStepRunner(object):
             g_rela = g_rela + g_ar8 @ lay["Wr8"] + self.onehot.t() @ (g_aq8 @ lay["Wqr8"])
             grads[pre + "rela_embed.weight"] = g_rela
             if hidden_prev is not None:
-                grads[pre + "Ws_attn.weight"] = _tn(g_as8.contiguous(), hidden_prev)[:a]
+                grads[pre + "Ws_attn.weight"] = _tn(g_as8.contiguous(), hidden_prev[:cap_in])[:a]
                 # g_hidden(prev) = edge part + attention-projection part + GRU state part (scattered in place)
                 check(lib.rg_scatter_rows(d, cap, ptr(lay["n_dev"]), ptr(lay["src"]), ptr(g_h0), ptr(g_hid_e), 1, st()))
                 _lib.Stats.launches += 1
@@ -222,23 +248,68 @@ class TrainStepRunner(object):
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        full = (self.cap,) * self.n_layer
         with torch.cuda.stream(side), torch.no_grad():       # eager warm-up (lazy inits, workspaces)
             self._forward()
-            self._backward()
+            self._backward(full)
         cur.wait_stream(side)
         torch.cuda.synchronize()
-        self.fwd_graph, self.bwd_graph = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.fwd_graph = torch.cuda.CUDAGraph()
         before = _lib.Stats.launches
         with torch.no_grad():
             with torch.cuda.graph(self.fwd_graph):
                 self.scores = self._forward()
-            mid = _lib.Stats.launches
-            with torch.cuda.graph(self.bwd_graph, pool=self.fwd_graph.pool()):
-                self._backward()
         # kernels of THIS library inside each graph (added to the bookkeeping at every replay)
-        self.fwd_launches, self.bwd_launches = mid - before, _lib.Stats.launches - mid
+        self.fwd_launches = _lib.Stats.launches - before
         _lib.Stats.launches = before
         self.frontiers = [lay["fr_out"] for lay in self.L]
+        self._capture_backward(full, warm=False)
+
+    # captured backward variants per runner (each owns its temporaries); REDGNN_BWD_VARIANTS=1 keeps only
+    # the full-capacity one (A/B measurements)
+    MAX_BWD_VARIANTS = int(os.environ.get("REDGNN_BWD_VARIANTS", "6"))
+    CALIBRATION_STEPS = 8      # new variants are only captured during the first replays of a runner
+
+    def node_counts(self):
+        """True node count of every layer of the forward just replayed (synchronises)."""
+        c = torch.stack([fr.counts[_lib.RG_CNT_N_OUT] for fr in self.frontiers]).cpu()
+        return [int(x) for x in c]
+
+    def caps_for(self, counts):
+        return tuple(next((c for c in self.ladder if c >= k), self.cap) for k in counts)
+
+    def _capture_backward(self, caps, warm=True):
+        if warm:                                             # new GEMM shapes: lazy library inits outside capture
+            cur, side = torch.cuda.current_stream(), torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side), torch.no_grad():
+                self._backward(caps)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        before = _lib.Stats.launches
+        with torch.no_grad(), torch.cuda.graph(g, pool=self.fwd_graph.pool()):
+            self._backward(caps)
+        launches = _lib.Stats.launches - before
+        _lib.Stats.launches = before
+        self.bwd_graphs[caps] = (g, launches)
+
+    def replay_backward(self):
+        """Replay the cheapest captured variant whose per-layer capacities cover this step's node
+        counts (the full-capacity variant always does).  During the first CALIBRATION_STEPS replays a
+        tighter variant (10 % headroom, next ladder step) is captured when the best one processes more
+        than 1.2x the rows it would."""
+        counts = self.node_counts()
+        best = min((k for k in self.bwd_graphs if all(c >= n for c, n in zip(k, counts))), key=sum)
+        if self.bwd_replays < self.CALIBRATION_STEPS and len(self.bwd_graphs) < self.MAX_BWD_VARIANTS:
+            want = self.caps_for([min(self.cap, n + n // 10 + 1) for n in counts])
+            if sum(best) > 1.2 * sum(want):
+                self._capture_backward(want)
+                best = want
+        self.bwd_replays += 1
+        g, launches = self.bwd_graphs[best]
+        g.replay()
+        _lib.Stats.launches += launches
 
 
 class TrainStepFunction(torch.autograd.Function):
@@ -263,8 +334,7 @@ class TrainStepFunction(torch.autograd.Function):
                                "the same batch size before its backward; set model.graph_train = False for "
                                "interleaved forward passes")
         r.g_out.copy_(g_scores)
-        r.bwd_graph.replay()
-        _lib.Stats.launches += r.bwd_launches
+        r.replay_backward()
         flat = r.flat_grad.clone()
         out, off = [], 0
         for k in r.names:
