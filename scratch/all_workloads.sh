@@ -1,7 +1,7 @@
 #!/bin/bash
 # one bench line per BASELINE-shaped workload -> gpurun_out/w_<name>_<mode>.json
 mkdir -p gpurun_out
-run() { name=$1; shift; python bench.py "$@" --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/w_$name.json 2>/dev/null; echo "$name rc=$?"; }
+run() { name=$1; shift; python bench.py "$@" --steps 10 --warmup 10 --no-cpu-baseline > gpurun_out/w_$name.json 2>/dev/null; echo "$name rc=$?"; }
 run family_eval --workload family
 run family_train --workload family --train --batch 20
 run fb237v2_eval --workload fb237v2
