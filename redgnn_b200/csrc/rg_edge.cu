@@ -590,13 +590,9 @@ __device__ __forceinline__ void bwd_range(const rg_segments &S, int64_t seg, int
                     G[v].y += ag.y;
                     G[v].z += ag.z;
                     G[v].w += ag.w;
-#ifndef RG_EXP_NO_RELA_RED
                     atomicAdd(gr + v * 4 + ql, ag);
-#endif
                 }
-#ifndef RG_EXP_NO_AR8_RED
                 atomicAdd(reinterpret_cast<float2 *>(g_ar8 + (size_t)r * 8) + ql, gz);
-#endif
             }
         }
     }
