@@ -105,3 +105,26 @@ def test_reference_base_model_resolves_to_this_package(setting, cls, tiny_dir, i
             sys.modules.pop(k, None)
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_vectorised_query_grouping_equals_the_reference_row_loop():
+    """data._group_queries (lexsort + split) against the reference's sort + dict loop
+    (transductive/load_data.py:91-104) on random, duplicate-heavy and empty inputs."""
+    from collections import defaultdict
+    from redgnn_b200.data import _group_queries
+
+    def naive(triples):
+        triples = [list(map(int, t)) for t in triples]
+        triples.sort(key=lambda x: (x[0], x[1]))
+        table = defaultdict(list)
+        for h, r, t in triples:
+            table[(h, r)].append(t)
+        return list(table.keys()), [np.array(v) for v in table.values()]
+
+    rng = np.random.default_rng(0)
+    for n, hi in ((0, 5), (1, 5), (50, 3), (500, 7), (2000, 40)):
+        tri = rng.integers(0, hi, size=(n, 3))
+        keys, ans = _group_queries(tri.tolist())
+        keys0, ans0 = naive(tri.tolist())
+        assert keys == keys0
+        assert len(ans) == len(ans0) and all(np.array_equal(a, b) for a, b in zip(ans, ans0))
