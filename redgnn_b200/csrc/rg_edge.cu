@@ -15,6 +15,9 @@
 
 namespace {
 
+#ifndef RG_FWD_MINBLOCKS
+#define RG_FWD_MINBLOCKS 5  // CTAs per SM the non-persistent forward is compiled for (48 registers)
+#endif
 constexpr int kWarpsPerBlock = 8;
 constexpr int kBlock = kWarpsPerBlock * 32;
 
@@ -343,7 +346,7 @@ __device__ __forceinline__ void fwd_block8(const rg_segments &S, int64_t seg0, i
 }
 
 template <int D, bool HAS_HIDDEN, bool IMPLICIT, bool BLOCK8>
-__global__ void __launch_bounds__(kBlock, 5) k_edge_fwd(rg_segments S, const float *__restrict__ hidden,
+__global__ void __launch_bounds__(kBlock, RG_FWD_MINBLOCKS) k_edge_fwd(rg_segments S, const float *__restrict__ hidden,
                                                      const float *__restrict__ as8, const float *__restrict__ rela,
                                                      const float *__restrict__ ar8, const float *__restrict__ aq8,
                                                      const float *__restrict__ w8, const float *__restrict__ b_alpha,
