@@ -413,6 +413,10 @@ __device__ __forceinline__ void stage_tables(unsigned long long *tab_bar, float 
 #define RG_PWARPS 16
 #endif
 constexpr int kPWarps = RG_PWARPS;
+#ifndef RG_PWARPS_BWD
+#define RG_PWARPS_BWD 12
+#endif
+constexpr int kPWarpsB = RG_PWARPS_BWD;  // persistent backward: 12 warps x 2 CTAs = 85 registers, no spills (-7 % vs 16)
 
 template <int D, bool HAS_HIDDEN>
 __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, const float *__restrict__ hidden,
@@ -811,7 +815,7 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
 // Persistent variant (implicit path): warps loop over segments on their own, so a block never idles
 // behind its longest segment, and the relation tables are read from shared memory (see k_edge_fwd_p).
 template <int D, bool HAS_HIDDEN>
-__global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_bwd_p(rg_segments S, const float *__restrict__ hidden,
+__global__ void __launch_bounds__(kPWarpsB * 32, 2) k_edge_bwd_p(rg_segments S, const float *__restrict__ hidden,
                                                                const float *__restrict__ as8,
                                                                const float *__restrict__ rela,
                                                                const float *__restrict__ ar8,
@@ -830,8 +834,8 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_bwd_p(rg_segments S, c
     const int lane = threadIdx.x & 31;
     const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
     const float ba = __ldg(b_alpha);
-    for (int64_t seg = (int64_t)blockIdx.x * kPWarps + (threadIdx.x >> 5); seg < n_true;
-         seg += (int64_t)gridDim.x * kPWarps) {
+    for (int64_t seg = (int64_t)blockIdx.x * kPWarpsB + (threadIdx.x >> 5); seg < n_true;
+         seg += (int64_t)gridDim.x * kPWarpsB) {
         SegRange r = seg_range<true>(S, seg);
         int hi = r.hi;
         if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
@@ -969,11 +973,11 @@ int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, co
             int dev = 0, n_sm = 148, per_sm = 1;
             RG_CUDA_CALL(cudaGetDevice(&dev));
             RG_CUDA_CALL(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-            RG_CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPWarps * 32, tab_bytes));
+            RG_CUDA_CALL(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPWarpsB * 32, tab_bytes));
             if (per_sm >= 1) {
-                const int64_t want = rg_cdiv(seg->n_seg, kPWarps);
+                const int64_t want = rg_cdiv(seg->n_seg, kPWarpsB);
                 const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)n_sm * per_sm);
-                kern<<<grid, kPWarps * 32, tab_bytes, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,
+                kern<<<grid, kPWarpsB * 32, tab_bytes, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,
                                                             g_hidden, node_small, g_rela, g_ar8, copies, H, has_heavy);
                 RG_LAUNCH_CHECK();
                 persistent = true;
