@@ -3,17 +3,20 @@
 
 A "step" is one pass of the hot path (per-layer frontier expansion + fused attention message
 passing + node update + score scatter, i.e. RED_GNN_trans.forward) over one batch of queries of a
-synthetic KG of the BASELINE shape.  Default workload = BASELINE.json configs[2]: FB15k-237-shaped
-synthetic KG (14,541 entities, 237 relations + inverses, 272,115 triples), n_layer=4, hidden 48,
-attn 5, filtered-eval forward, per-GPU query batch fixed (weak scaling over 1/2/4/8 GPUs).
+KG of the BASELINE shape.  Default workload = BASELINE.json configs[2]: FB15k-237-shaped synthetic KG
+(14,541 entities, 237 relations + inverses, 272,115 triples), n_layer=4, hidden 48, attn 5,
+filtered-eval forward, per-GPU query batch fixed (weak scaling over 1/2/4/8 GPUs).  The same line
+carries `subsystems.train`: forward + backward + Adam (+ NCCL gradient all-reduce when N > 1) on the
+same KG, measured in the same run.
 
   python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path)
-  python bench.py --impl reference --steps K --warmup W    # reference algorithm on host cores (oracle port)
+  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path on the host cores
 
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte model behind `roofline`.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte models behind `roofline`.
 """
 import argparse
 import contextlib
+import hashlib
 import io
 import json
 import os
@@ -30,19 +33,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOADS = {  # name -> (synth shape, n_layer, default per-GPU batch)
-    "fb15k237": ("fb15k237", 4, 64),
-    "family": ("family", 3, 256),
-    "yago310": ("yago310", 5, 8),
-    "tiny": ("tiny", 3, 32),
-    "powerlaw": ("powerlaw", 6, 4),      # built from arrays (ArrayLoader): 10 M triples, no text round trip
+import kg_synth  # noqa: E402  (numpy only: the reference arm must not load the CUDA library)
+
+WORKLOADS = {  # name -> (synth shape, n_layer, eval queries per GPU per step, train queries per GPU per step)
+    "fb15k237": ("fb15k237", 4, 64, 16),
+    "family": ("family", 3, 256, 20),       # bundled Static/transductive/data/family when staged (configs[0])
+    "yago310": ("yago310", 5, 8, 4),
+    "tiny": ("tiny", 3, 32, 8),
+    "powerlaw": ("powerlaw", 6, 4, 2),      # built from arrays (ArraySplits): 10 M triples, no text round trip
+    "fb237v2": ("fb237v2", 3, 128, 10),     # bundled Static/inductive/data/fb237_v2(+_ind) when staged (configs[1])
 }
 ARRAY_WORKLOADS = ("powerlaw",)
-# BASELINE configs[1]: Static/inductive on an fb237_v2-shaped pair of KGs (train graph 2,608 entities /
-# 9,739 triples, unseen-entity graph 1,660 entities / 4,145 triples, 200 relations), n_layer 3
+# synthetic stand-in for BASELINE configs[1] when the bundled pair is not staged: train graph 2,608 entities /
+# 9,739 triples, unseen-entity graph 1,660 entities / 4,145 triples, 200 relations
 INDUCTIVE_WORKLOADS = {"fb237v2": dict(n_ent=2608, n_ent_ind=1660, n_rel=200, n_train=9739, n_ind_train=4145,
                                        n_eval=1170)}
-WORKLOADS["fb237v2"] = ("fb237v2", 3, 128)
+BUNDLED = {"family": ("transductive", "family"), "fb237v2": ("inductive", "fb237_v2")}
 HIDDEN, ATTN = 48, 5
 
 
@@ -54,18 +60,68 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="fb15k237", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="queries per GPU per step (0 = workload default)")
-    ap.add_argument("--train", action="store_true", help="time forward+backward+Adam instead of eval forward")
+    ap.add_argument("--train", action="store_true", help="headline = forward+backward+Adam instead of eval forward")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-subsystem", action="store_true", help="skip the subsystems.train block of an eval run")
+    ap.add_argument("--synthetic", action="store_true", help="family / fb237v2: shaped synthetic KG even if the bundled "
+                                                             "dataset is staged")
     ap.add_argument("--cpu-queries", type=int, default=2, help="queries per reference/CPU step (bounded sample)")
     return ap.parse_args()
 
 
-def make_dataset(workload):
-    from redgnn_b200 import synth
-    shape, n_layer, batch = WORKLOADS[workload]
+# ------------------------------------------------------------------------------------------------
+# workload description shared by both arms (identical `config` => the driver's same_config holds)
+# ------------------------------------------------------------------------------------------------
+def bundled_dir(workload, args):
+    """Directory of the bundled dataset (oracle/_ref staged copy or the mounted reference) or None."""
+    if args.synthetic or workload not in BUNDLED:
+        return None
+    from oracle import ref_import as R
+    if not R.available():
+        return None
+    setting, name = BUNDLED[workload]
+    d = R.data_dir(setting, name)
+    return d if os.path.isdir(d) else None
+
+
+def dataset_for(workload, args):
+    """-> (task_dir | None for array workloads, data description, inductive?)"""
+    inductive = workload in INDUCTIVE_WORKLOADS
+    d = bundled_dir(workload, args)
+    if d is not None:
+        return d, "bundled (reference Static/%s/data/%s)" % BUNDLED[workload], inductive
+    if workload in ARRAY_WORKLOADS:
+        return None, "synthetic", False
     tmp = tempfile.mkdtemp(prefix="rg_bench_")
-    task = synth.write_transductive(os.path.join(tmp, shape), shape, seed=0)
-    return task, n_layer, batch
+    if inductive:
+        return kg_synth.write_inductive(os.path.join(tmp, workload), seed=0, **INDUCTIVE_WORKLOADS[workload]), \
+            "synthetic", True
+    shape = WORKLOADS[workload][0]
+    return kg_synth.write_transductive(os.path.join(tmp, shape), shape, seed=0), "synthetic", False
+
+
+def workload_name(workload, n_layer, data):
+    if data.startswith("bundled"):
+        setting, name = BUNDLED[workload]
+        return "bundled %s dataset (Static/%s/data/%s), n_layer=%d" % (name, setting, name, n_layer)
+    if workload in INDUCTIVE_WORKLOADS:
+        w = INDUCTIVE_WORKLOADS[workload]
+        return ("%s-shaped synthetic inductive pair (train KG %d entities / %d triples, unseen-entity KG %d entities "
+                "/ %d triples, %d relations + inverses), n_layer=%d" % (
+                    workload, w["n_ent"], w["n_train"], w["n_ent_ind"], w["n_ind_train"], w["n_rel"], n_layer))
+    ne, nr, nt = kg_synth.SHAPES[WORKLOADS[workload][0]][:3]
+    return "%s-shaped synthetic KG (%d entities, %d relations + inverses, %d triples), n_layer=%d" % (
+        workload, ne, nr, nt, n_layer)
+
+
+def config_of(args, data):
+    """The SAME dict in the CUDA arm and the reference arm: names the workload and the step."""
+    _, n_layer, batch, tbatch = WORKLOADS[args.workload]
+    per_gpu = args.batch or (tbatch if args.train else batch)
+    return {"workload": workload_name(args.workload, n_layer, data),
+            "step": "forward + backward + Adam" if args.train else "filtered-eval forward",
+            "queries_per_gpu_per_step": per_gpu, "queries_per_step": per_gpu * args.gpus,
+            "hidden_dim": HIDDEN, "attn_dim": ATTN, "n_layer": n_layer, "parallelism": "dp%d" % args.gpus}
 
 
 def peaks():
@@ -74,6 +130,12 @@ def peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_build_id():
+    """Identifies the edge-kernel source a committed ncu capture belongs to."""
+    with open(os.path.join(ROOT, "redgnn_b200", "csrc", "rg_edge.cu"), "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:12]
 
 
 class ClockSampler(object):
@@ -124,87 +186,153 @@ class ClockSampler(object):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_step(oracle, data, sd, n_layer, subs, rels):
-    """One step of the reference algorithm on host cores (oracle port: scipy SpGEMM + torch.unique +
-    torch CPU ops, same library calls as the reference)."""
-    with torch.no_grad():
-        scores, trace = oracle.model_forward(sd, data.test_graph, subs, rels, n_layer, "relu", return_trace=True)
-    return scores, sum(int(t[1].shape[0]) for t in trace)
+# ------------------------------------------------------------------------------------------------
+# the reference's CPU path (the `--impl reference` arm and the `cpu_baseline` leg of the CUDA arm)
+# ------------------------------------------------------------------------------------------------
+class CpuReference(object):
+    """forward(subs, rels) -> edges expanded, through
+      kind "reference": the reference's OWN modules (Static/<setting>/{load_data,models}.py, unmodified;
+                        oracle/_ref staged copy on the GPU box) under the three shims of
+                        oracle/ref_import.py, `.cuda()` forced to the identity = its CPU path;
+      kind "port":      oracle/redgnn_oracle.py (same scipy / torch-CPU calls), for the array-built
+                        workloads whose 10 M triples the reference's row-by-row text loader cannot
+                        ingest in bench time, or when no reference copy is staged."""
+
+    def __init__(self, workload, task, inductive, n_layer, train=False):
+        from oracle import redgnn_oracle as O
+        from oracle import ref_import as R
+        self.train, self.n_layer, self.inductive = train, n_layer, inductive
+        self.edges = 0
+        if task is not None and R.available():
+            self.kind = "reference"
+            setting = "inductive" if inductive else "transductive"
+            _, M, _ = R.load_reference(setting, force_cpu=True)
+            self.loader = R.make_loader(setting, task)
+            opts = R.Options()
+            opts.hidden_dim, opts.attn_dim, opts.n_layer, opts.dropout, opts.act = HIDDEN, ATTN, n_layer, 0.0, "relu"
+            opts.n_rel = self.loader.n_rel
+            torch.manual_seed(1234)
+            self.model = (M.RED_GNN_induc if inductive else M.RED_GNN_trans)(opts, self.loader)
+            self.model.train() if train else self.model.eval()
+            inner = self.loader.get_neighbors
+
+            def counting(*a, **k):
+                out = inner(*a, **k)
+                self.edges += int(out[1].shape[0])
+                return out
+            self.loader.get_neighbors = counting
+            self.test_q = np.array(self.loader.test_q)
+            self.train_rows = np.array(self.loader.get_batch(np.arange(min(4096, self.loader.n_train))))
+            self.optim = torch.optim.Adam(self.model.parameters(), lr=1e-3) if train else None
+        else:
+            self.kind = "port"
+            self.O = O
+            if task is None:
+                sp = kg_synth.ArraySplits(WORKLOADS[workload][0], seed=0)
+                self.graph = O.Graph(sp.train_graph_triples if train else sp.test_graph_triples, sp.n_ent, sp.n_rel)
+                self.test_q, self.train_rows, n_rel, self.n_ent_out = np.array(sp.test_q), sp.train_data[:4096], sp.n_rel, None
+            elif inductive:
+                ind = O.InductiveData(task)
+                self.graph = ind.tra_graph if train else ind.ind_graph
+                self.test_q, self.train_rows, n_rel = np.array(ind.test_q), ind.train_data, ind.n_rel
+                self.n_ent_out = None if train else ind.n_ent_ind
+            else:
+                data = O.TransductiveData(task)
+                self.graph = data.graph if train else data.test_graph
+                self.test_q, self.train_rows, n_rel, self.n_ent_out = np.array(data.test_q), data.train_data, data.n_rel, None
+            self.sd = O.init_state_dict(n_layer, HIDDEN, ATTN, n_rel, seed=1234)
+            if train:
+                self.sd = {k: v.clone().requires_grad_(True) for k, v in self.sd.items()}
+                self.optim = torch.optim.Adam(list(self.sd.values()), lr=1e-3)
+
+    def queries(self, i, nq):
+        rows = self.train_rows if self.train else self.test_q
+        k = (i * nq) % max(1, len(rows) - nq)
+        return rows[k:k + nq]
+
+    def step(self, q):
+        """One step on the host cores; returns the number of edges expanded."""
+        self.edges = 0
+        if self.kind == "reference":
+            if self.train:                                    # base_model.py:54-62
+                self.model.zero_grad()
+                scores = self.model(q[:, 0], q[:, 1])
+                pos = scores[torch.arange(len(scores)), torch.as_tensor(q[:, 2])]
+                mx = torch.max(scores, 1, keepdim=True)[0]
+                loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(scores - mx), 1)))
+                loss.backward()
+                self.optim.step()
+            else:
+                with torch.no_grad():                         # evaluate() only reads .data (base_model.py:106)
+                    if self.inductive:
+                        self.model(q[:, 0], q[:, 1], "inductive")
+                    else:
+                        self.model(q[:, 0], q[:, 1], mode="test")
+            return self.edges
+        O = self.O
+        if self.train:
+            self.optim.zero_grad()
+            scores, trace = O.model_forward(self.sd, self.graph, q[:, 0], q[:, 1], self.n_layer, "relu", return_trace=True)
+            O.train_loss(scores, q[:, 2]).backward()
+            self.optim.step()
+        else:
+            with torch.no_grad():
+                _, trace = O.model_forward(self.sd, self.graph, q[:, 0], q[:, 1], self.n_layer, "relu",
+                                           n_ent_out=self.n_ent_out, return_trace=True)
+        return sum(int(t[1].shape[0]) for t in trace)
+
+    def describe(self):
+        if self.kind == "reference":
+            return "the reference's own Static/*/load_data.py + models.py on the host cores (scipy SpGEMM + torch.unique + torch CPU)"
+        return "oracle port of the reference CPU path (same scipy SpGEMM + torch.unique + torch CPU calls)"
+
+
+def timed_cpu_sample(ref, nq, budget_s, min_reps=3, max_reps=50):
+    ref.step(ref.queries(0, nq))                                        # warm-up
+    t0 = time.perf_counter()
+    reps, edges = 0, 0
+    while reps < min_reps or (time.perf_counter() - t0 < budget_s and reps < max_reps):
+        edges += ref.step(ref.queries(reps + 1, nq))
+        reps += 1
+    return reps, edges, time.perf_counter() - t0
 
 
 def run_reference(args):
     """--impl reference: rank 0 only; the other ranks exit 0 without work."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    from oracle import redgnn_oracle as O
-    if args.workload in ARRAY_WORKLOADS:
-        from redgnn_b200 import synth
-
-        class _D(object):
-            pass
-        ld = synth.ArrayLoader(WORKLOADS[args.workload][0], seed=0, device="cpu")
-        n_layer = WORKLOADS[args.workload][1]
-        data = _D()
-        data.test_graph = O.Graph(ld._test_graph.triples, ld.n_ent, ld.n_rel)
-        data.test_q, data.n_rel = ld.test_q, ld.n_rel
-    elif args.workload in INDUCTIVE_WORKLOADS:
-        from redgnn_b200 import synth
-
-        class _D(object):
-            pass
-        n_layer = WORKLOADS[args.workload][1]
-        task = synth.write_inductive(os.path.join(tempfile.mkdtemp(prefix="rg_bench_"), args.workload), seed=0,
-                                     **INDUCTIVE_WORKLOADS[args.workload])
-        ind = O.InductiveData(task)
-        data = _D()
-        data.test_graph, data.test_q, data.n_rel = ind.ind_graph, ind.test_q, ind.n_rel
-    else:
-        task, n_layer, _ = make_dataset(args.workload)
-        data = O.TransductiveData(task)
-    sd = O.init_state_dict(n_layer, HIDDEN, ATTN, data.n_rel, seed=1234)
+    _, n_layer, _, _ = WORKLOADS[args.workload]
+    task, data, inductive = dataset_for(args.workload, args)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    q = np.array(data.test_q)
+    ref = CpuReference(args.workload, task, inductive, n_layer, train=args.train)
     nq = max(1, args.cpu_queries)
     # bounded sample: if the first step projects the whole --steps/--warmup run beyond ~4 minutes, a step
     # shrinks to one query (the metric is per query, so the value is unaffected)
     t0 = time.perf_counter()
-    cpu_reference_step(O, data, sd, n_layer, q[:nq, 0], q[:nq, 1])
+    ref.step(ref.queries(0, nq))
     if nq > 1 and (time.perf_counter() - t0) * (args.warmup + args.steps) > 240.0:
         nq = 1
-    batches = [q[i * nq:(i + 1) * nq] for i in range(args.warmup + args.steps)]
-    for b in batches[:max(0, args.warmup - 1)]:
-        cpu_reference_step(O, data, sd, n_layer, b[:, 0], b[:, 1])
+    for i in range(max(0, args.warmup - 1)):
+        ref.step(ref.queries(i + 1, nq))
     t0 = time.perf_counter()
     edges = 0
-    for b in batches[args.warmup:]:
-        edges += cpu_reference_step(O, data, sd, n_layer, b[:, 0], b[:, 1])[1]
+    for i in range(args.steps):
+        edges += ref.step(ref.queries(args.warmup + i, nq))
     dt = time.perf_counter() - t0
     qps = nq * args.steps / dt
-    sample = "%d queries/step x %d steps of the %s workload, oracle port of the reference CPU path" % (
-        nq, args.steps, args.workload)
+    cfg = config_of(args, data)
+    sample = ("%d of the %d queries of a step (a CPU step over all of them would take ~%.0f s), x %d steps; %s" % (
+        nq, cfg["queries_per_step"], cfg["queries_per_step"] / qps, args.steps, ref.describe()))
     emit({
         "impl": "reference", "metric": "queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "edges_per_s": edges / dt,
-        "config": {"workload": workload_name(args.workload, n_layer), "queries_per_step": nq,
-                   "hidden_dim": HIDDEN, "attn_dim": ATTN, "n_layer": n_layer},
-        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": data,
+        "edges_per_s": edges / dt, "config": cfg,
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": ref.kind, "sample": sample,
+                         "queries_per_cpu_step": nq},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
-
-
-def workload_name(workload, n_layer):
-    from redgnn_b200 import synth
-    if workload in INDUCTIVE_WORKLOADS:
-        w = INDUCTIVE_WORKLOADS[workload]
-        return ("%s-shaped synthetic inductive pair (train KG %d entities / %d triples, unseen-entity KG %d entities "
-                "/ %d triples, %d relations + inverses), n_layer=%d, eval forward on the unseen-entity graph" % (
-                    workload, w["n_ent"], w["n_train"], w["n_ent_ind"], w["n_ind_train"], w["n_rel"], n_layer))
-    ne, nr, nt = synth.SHAPES[WORKLOADS[workload][0]][:3]
-    return "%s-shaped synthetic KG (%d entities, %d relations + inverses, %d triples), n_layer=%d, eval forward" % (
-        workload, ne, nr, nt, n_layer)
 
 
 _REAL_STDOUT = None
@@ -228,143 +356,244 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
-def main():
-    args = parse_args()
-    guard_stdout()
-    if args.impl == "reference":
-        return run_reference(args)
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def train_loss(scores, objs, dev):
+    """base_model.py:58-60."""
+    pos = scores[torch.arange(len(scores), device=dev), objs]
+    mx = scores.max(1, keepdim=True)[0]
+    return torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(scores - mx), 1)))
 
-    import torch.distributed as dist
-    import redgnn_b200
-    from redgnn_b200 import synth, _lib
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+class Bench(object):
+    """State shared by the measurements of one process (one GPU)."""
 
-    inductive = args.workload in INDUCTIVE_WORKLOADS
-    if args.workload in ARRAY_WORKLOADS:
-        shape, n_layer, batch = WORKLOADS[args.workload]
-        loader, task = synth.ArrayLoader(shape, seed=0, device=dev), None
-    elif inductive:
-        _, n_layer, batch = WORKLOADS[args.workload]
-        task = synth.write_inductive(os.path.join(tempfile.mkdtemp(prefix="rg_bench_"), args.workload), seed=0,
-                                     **INDUCTIVE_WORKLOADS[args.workload])
-        with contextlib.redirect_stdout(io.StringIO()):
-            loader = redgnn_b200.InductiveLoader(task, device=dev)
-    else:
-        task, n_layer, batch = make_dataset(args.workload)
-        with contextlib.redirect_stdout(io.StringIO()):
-            loader = redgnn_b200.TransductiveLoader(task, device=dev)
-    batch = args.batch or batch
-    opts = synth.Options(hidden_dim=HIDDEN, attn_dim=ATTN, n_layer=n_layer, n_rel=loader.n_rel, dropout=0.0)
-    torch.manual_seed(1234)
-    model = (redgnn_b200.RED_GNN_induc if inductive else redgnn_b200.RED_GNN_trans)(opts, loader).to(dev)
-    optim = torch.optim.Adam(model.parameters(), lr=1e-3) if args.train else None
-    model.train() if args.train else model.eval()
-    if inductive:       # train on the training graph, evaluate on the unseen-entity graph
-        mode = "transductive" if args.train else "inductive"
-    else:
-        mode = "train" if args.train else "test"
+    def __init__(self, args):
+        import torch.distributed as dist
+        import redgnn_b200
+        from redgnn_b200 import synth, _lib
+        self.args, self.dist, self.pkg, self._lib = args, dist, redgnn_b200, _lib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+        torch.cuda.set_device(self.local)
+        self.dev = dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=dev)
+        self.task, self.data, self.inductive = dataset_for(args.workload, args)
+        shape, self.n_layer, self.batch_eval, self.batch_train = WORKLOADS[args.workload]
+        if self.task is None:
+            self.loader = synth.ArrayLoader(shape, seed=0, device=dev)
+        else:
+            with contextlib.redirect_stdout(io.StringIO()):
+                cls = redgnn_b200.InductiveLoader if self.inductive else redgnn_b200.TransductiveLoader
+                self.loader = cls(self.task, device=dev)
+        self.opts = synth.Options(hidden_dim=HIDDEN, attn_dim=ATTN, n_layer=self.n_layer, n_rel=self.loader.n_rel,
+                                  dropout=0.0)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+        self.peak, self.peak_src = peaks()
 
-    # query stream: rank r takes batches r, r+world, ... of the test queries (train triples for --train)
-    if args.train:
-        pool = (loader.tra_train if inductive else loader.train_data)[:, :3]
-    else:
-        tq = np.array(loader.test_q)
-        pool = np.concatenate([tq, np.zeros((len(tq), 1), dtype=tq.dtype)], 1)
-    n_steps_total = args.warmup + args.steps
-    need = batch * world * n_steps_total * 2
-    reps = -(-need // len(pool))
-    pool = np.concatenate([pool] * reps, 0)
+    def new_model(self, train):
+        torch.manual_seed(1234)
+        cls = self.pkg.RED_GNN_induc if self.inductive else self.pkg.RED_GNN_trans
+        model = cls(self.opts, self.loader).to(self.dev)
+        model.train() if train else model.eval()
+        model.check_tensor_inputs = False       # device-resident query ids: no host read-back in the step
+        model.grads_in_place = True             # captured training step writes .grad in place (flat buffer)
+        return model
 
-    def step_batch(phase, i):
-        k = ((phase * n_steps_total + i) * world + rank) * batch
+    def mode(self, train):
+        if self.inductive:       # train on the training graph, evaluate on the unseen-entity graph
+            return "transductive" if train else "inductive"
+        return "train" if train else "test"
+
+    def pool(self, train, batch, n_steps_total):
+        """Query stream: rank r takes batches r, r+world, ... of the test queries (train triples for train)."""
+        if train:
+            pool = np.asarray(self.loader.tra_train if self.inductive else self.loader.train_data)[:, :3]
+        else:
+            tq = np.array(self.loader.test_q)
+            pool = np.concatenate([tq, np.zeros((len(tq), 1), dtype=tq.dtype)], 1)
+        need = batch * self.world * n_steps_total * 2
+        return np.concatenate([pool] * (-(-need // len(pool))), 0)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+
+def measure(B, train, batch, headline):
+    """Times `steps` steps (eval forward, or forward+backward+all-reduce+Adam) with CUDA events per step,
+    an instrumented pass for the per-kernel times, and (headline only) the end-to-end pass through the
+    public API with host buffers.  Returns a dict of raw results (this rank)."""
+    args, dev, _lib, dist, world, rank = B.args, B.dev, B._lib, B.dist, B.world, B.rank
+    from redgnn_b200 import dist as rgd
+    model = B.new_model(train)
+    optim = torch.optim.Adam(model.parameters(), lr=1e-3) if train else None
+    mode = B.mode(train)
+    n_total = args.warmup + args.steps
+    pool = B.pool(train, batch, n_total)
+    ar_events = []
+
+    def step_batch(phase, i, r=None):
+        k = ((phase * n_total + i) * world + (rank if r is None else r)) * batch
         return pool[k:k + batch]
 
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-
-    def run_step(subs, rels, objs):
-        if args.train:
+    def run_step(subs, rels, objs, time_allreduce=False):
+        if train:
             optim.zero_grad(set_to_none=True)
-            scores = model(subs, rels, mode)
-            pos = scores[torch.arange(len(scores), device=dev), objs]
-            mx = scores.max(1, keepdim=True)[0]
-            loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(scores - mx), 1)))
+            loss = train_loss(model(subs, rels, mode), objs, dev)
             loss.backward()
             if world > 1:
-                flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-                dist.all_reduce(flat)            # SUM: the loss is a sum over queries
-                off = 0
-                for p in model.parameters():
-                    p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                    off += p.numel()
+                if time_allreduce:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                rgd.allreduce_model_gradients(model)        # SUM: the loss is a sum over queries
+                if time_allreduce:
+                    e1.record()
+                    ar_events.append((e0, e1))
             optim.step()
             return loss
         with torch.no_grad():
             return model(subs, rels, mode=mode)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    to_dev = lambda b: tuple(torch.as_tensor(b[:, c].astype(np.int64)).to(dev) for c in range(3))
+    res = {"batch": batch, "train": train}
 
-    # ---------------- device-resident timing (value) ----------------
-    dev_batches = []
-    for i in range(n_steps_total):
-        b = step_batch(0, i)
-        dev_batches.append(tuple(torch.as_tensor(b[:, c].astype(np.int64)).to(dev) for c in range(3)))
-    sampler = ClockSampler(local)
-    if rank == 0:
+    # ---- N > 1 training: the all-reduced gradients equal the single-GPU gradients of the concatenated batch
+    if train and world > 1:
+        res["dist_check"] = dist_check(B, model, optim, mode, [step_batch(2, 0, r) for r in range(world)], batch)
+
+    dev_batches = [to_dev(step_batch(0, i)) for i in range(n_total)]
+    sampler = ClockSampler(B.local) if headline and rank == 0 else None
+    if sampler:
         sampler.start()
     for i in range(args.warmup):
         run_step(*dev_batches[i])
-    barrier()
+    B.barrier()
     _lib.Stats.launches = 0
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    edges_total = 0
-    barrier()
-    sampler.begin()
+    B.barrier()
+    if sampler:
+        sampler.begin()
     for i in range(args.steps):
-        flush.zero_()                                   # L2 flush between timed iterations (untimed)
+        B.flush.zero_()                                 # L2 flush between timed iterations (untimed)
         ev[i][0].record()
-        run_step(*dev_batches[args.warmup + i])
+        run_step(*dev_batches[args.warmup + i], time_allreduce=True)
         ev[i][1].record()
-    barrier()
-    sampler.end()
-    launches = _lib.Stats.launches
-    clocks = sampler.stop() if rank == 0 else None
-    t_dev = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    B.barrier()
+    if sampler:
+        sampler.end()
+        res["clocks"] = sampler.stop()
+    res["launches"] = _lib.Stats.launches
+    res["t_dev"] = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    res["allreduce_us"] = float(np.median([a.elapsed_time(b) for a, b in ar_events])) * 1e3 if ar_events else None
+    res["grad_bytes"] = int(sum(p.numel() for p in model.parameters()) * 4)
 
-    # dominant kernel: fused edge forward, timed with CUDA events around every rg_edge_agg_fwd launch in
-    # an instrumented pass over the SAME batches (the timed region above replays CUDA graphs, which
-    # cannot hold event records).  Algorithmic bytes per launch:
-    #   (16 + 4d) * E + 4d * N'   with the hidden-row gather (layers >= 1),  16 * E + 4d * N' at layer 0
+    # ---- per-kernel times: CUDA events around the named launches in an instrumented pass over the SAME
+    # batches (the timed region above replays CUDA graphs, which cannot hold event records)
     _lib.Stats.timing = []                            # routes every step through the eager, instrumented path
     for i in range(2):                                # untimed warm-up of exactly that path (allocator pools)
         run_step(*dev_batches[i])
-    barrier()
+    B.barrier()
     _lib.Stats.timing = []
+    edges_total = 0
     for i in range(args.steps):
-        flush.zero_()
+        B.flush.zero_()
         run_step(*dev_batches[args.warmup + i])
         edges_total += sum(model.last_stats["edges"])
-    barrier()
+    B.barrier()
     timing, _lib.Stats.timing = _lib.Stats.timing, None
-    # every step issues the same launches in the same order: per launch slot take the MEDIAN over the
-    # steps (one-off stalls of hundreds of ms were seen right after the nvidia-smi poller exits), then add
-    # the slots up -> milliseconds and algorithmic bytes of one step
+    res["edges_total"] = edges_total
+    res.update(kernel_breakdown(timing, args.steps))
+
+    # ---- end-to-end through the public API with host buffers
+    if headline:
+        host_batches = [step_batch(1, i) for i in range(n_total)]
+        n_ent_out = B.loader.n_ent_for(mode)
+        pinned_out = torch.empty((batch, n_ent_out), dtype=torch.float32).pin_memory()
+        pinned_obj = torch.empty(batch, dtype=torch.int64).pin_memory()
+        for i in range(args.warmup):
+            b = host_batches[i]
+            out = run_step(b[:, 0], b[:, 1], torch.as_tensor(b[:, 2]).to(dev))
+            if not train:
+                pinned_out.copy_(out)
+        B.barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            b = host_batches[args.warmup + i]
+            if train:
+                pinned_obj.copy_(torch.as_tensor(b[:, 2]))
+                loss = run_step(b[:, 0], b[:, 1], pinned_obj.to(dev, non_blocking=True))
+                loss.item()                                 # D2H read of the step's result
+            else:
+                out = run_step(b[:, 0], b[:, 1], None)      # numpy subs/rels: H2D inside model.forward
+                pinned_out.copy_(out, non_blocking=True)    # D2H of the (n, n_ent) score matrix
+                torch.cuda.current_stream().synchronize()
+        B.barrier()
+        res["t_e2e"] = time.perf_counter() - t0
+        res["h2d"] = int(batch * 16 + (batch * 8 if train else 0))
+        res["d2h"] = int(4 if train else batch * n_ent_out * 4)
+    res["model"] = model
+    res["first_batch"] = dev_batches[args.warmup]
+    return res
+
+
+def dist_check(B, model, optim, mode, shards, batch):
+    """Once, before timing: gradients of this rank's shard, all-reduced (SUM) over the ranks, against
+    rank 0's single-GPU gradients of the CONCATENATED batch (<= 1e-5 of the largest entry per tensor,
+    plus the fp32-atomics noise floor of the relation gradients)."""
+    from redgnn_b200 import dist as rgd
+    dev, world, rank = B.dev, B.world, B.rank
+    tri = shards[rank]
+    model.zero_grad(set_to_none=True)
+    train_loss(model(tri[:, 0], tri[:, 1], mode), torch.as_tensor(tri[:, 2]).to(dev), dev).backward()
+    rgd.allreduce_model_gradients(model)
+    got = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    verdict = torch.zeros(1, device=dev)
+    how = "concatenated"
+    if rank == 0:
+        cat = np.concatenate(shards, 0)
+        fits = len(cat) * B.loader.n_ent_for(mode) * HIDDEN * 4 * 9 * B.n_layer <= model.ASYNC_BUDGET_BYTES
+        model.zero_grad(set_to_none=True)
+        if fits:
+            train_loss(model(cat[:, 0], cat[:, 1], mode), torch.as_tensor(cat[:, 2]).to(dev), dev).backward()
+            want = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+        else:                                   # the concatenated batch does not fit one GPU: shard by shard
+            how = "accumulated shard by shard (concatenated batch exceeds the single-GPU buffer budget)"
+            want = {k: torch.zeros_like(p) for k, p in model.named_parameters()}
+            for s in shards:
+                model.zero_grad(set_to_none=True)
+                train_loss(model(s[:, 0], s[:, 1], mode), torch.as_tensor(s[:, 2]).to(dev), dev).backward()
+                for k, p in model.named_parameters():
+                    want[k] += p.grad
+        top = max(float(w.abs().max()) for w in want.values())
+        worst = 0.0
+        for k in want:
+            err = float((got[k] - want[k]).abs().max())
+            worst = max(worst, err / max(float(want[k].abs().max()), 1e-3 * top))
+        verdict[0] = worst
+    model.zero_grad(set_to_none=True)
+    B.dist.broadcast(verdict, 0)
+    worst = float(verdict[0])
+    assert worst <= 1e-5 or (worst <= 1e-4 and how != "concatenated"), \
+        "N-GPU gradients differ from the single-GPU gradients of the concatenated batch: rel err %.3e" % worst
+    return {"status": "ok", "max_rel_err": worst, "reference": how, "queries": int(batch * world)}
+
+
+def kernel_breakdown(timing, steps):
+    """Every step issues the same launches in the same order: per launch slot take the MEDIAN over the
+    steps (one-off stalls of hundreds of ms were seen right after the nvidia-smi poller exits), then add
+    the slots up -> milliseconds and algorithmic bytes of one step."""
     edge_ms, edge_bytes, bwd_ms, bwd_bytes = 0.0, 0.0, 0.0, 0.0
     kernel_ms = {}
-    per_step = len(timing) // max(1, args.steps)
+    per_step = len(timing) // max(1, steps)
     med = lambda xs: float(np.median(xs))
     for j in range(per_step):
-        slot = [timing[st * per_step + j] for st in range(args.steps)]
+        slot = [timing[st * per_step + j] for st in range(steps)]
         name = slot[0][0]
         ms = med([a.elapsed_time(b) for _, _, a, b in slot])
         kernel_ms[name] = kernel_ms.get(name, 0.0) + ms
@@ -380,6 +609,7 @@ def main():
             bwd_ms += ms
             bwd_bytes += med(nbytes)
         if name == "edge_fwd":
+            # (16 + 4d) * E + 4d * N'   with the hidden-row gather (layers >= 1),  16 * E + 4d * N' at layer 0
             nbytes = []
             for _, (seg, d, has_hidden), _, _ in slot:
                 fr = getattr(seg, "frontier", None)      # sync-free path: counts resolved by model.last_stats
@@ -387,18 +617,21 @@ def main():
                 nbytes.append(((16 + 4 * d) if has_hidden else 16) * e_l + 4 * d * n_seg)
             edge_ms += ms
             edge_bytes += med(nbytes)
-    t_instr = edge_ms * 1e-3 * args.steps          # same units as t_dev (all timed steps)
+    return {"kernel_ms": kernel_ms, "edge_ms": edge_ms, "edge_bytes": edge_bytes, "bwd_ms": bwd_ms,
+            "bwd_bytes": bwd_bytes}
 
-    # subsystem (1): the drop-in get_neighbors chain (explicit sampled_edges / tail_nodes / remap emission,
-    # reference load_data.py:106-131) over the first timed batch, device time per hop between CUDA events
-    # (the 16-byte count read-back between them is excluded).  Bytes: SURVEY 8(d) B_exp.
-    kg = loader.graph_for(mode, dev)
+
+def measure_expand(B, mode, batch, subs0):
+    """Subsystem (1): the drop-in get_neighbors chain (explicit sampled_edges / tail_nodes / remap emission,
+    reference load_data.py:106-131) over one batch, device time per hop between CUDA events (the
+    16-byte count read-back between them is excluded).  Bytes: SURVEY 8(d) B_exp."""
+    dev = B.dev
+    kg = B.loader.graph_for(mode, dev)
     exp_ms, exp_emit_ms, exp_bytes, exp_edges = 0.0, 0.0, 0.0, 0
     for rep in range(2):                                  # rep 0 = warm-up (allocator), rep 1 = measured
-        subs0 = dev_batches[args.warmup][0]
         nodes = torch.stack([torch.arange(batch, device=dev), subs0], 1)
         spans = []
-        for l in range(n_layer):
+        for l in range(B.n_layer):
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record()
             fr_in = kg.frontier_from_nodes(nodes, batch)
@@ -422,127 +655,130 @@ def main():
                 exp_emit_ms += e2.elapsed_time(e3)
                 exp_bytes += nbytes
                 exp_edges += n_e
-    del nodes, tail_nodes
+    return exp_ms, exp_emit_ms, exp_bytes, exp_edges
 
-    # ---------------- end-to-end timing through the public API with host buffers (e2e) ----------------
-    host_batches = [step_batch(1, i) for i in range(n_steps_total)]
-    n_ent_out = loader.n_ent_for(mode)
-    pinned_out = torch.empty((batch, n_ent_out), dtype=torch.float32).pin_memory()
-    for i in range(args.warmup):
-        b = host_batches[i]
-        out = run_step(b[:, 0], b[:, 1], torch.as_tensor(b[:, 2]).to(dev))
-        if not args.train:
-            pinned_out.copy_(out)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        b = host_batches[args.warmup + i]
-        if args.train:
-            loss = run_step(b[:, 0], b[:, 1], torch.as_tensor(b[:, 2]).to(dev))
-            loss.item()                                 # D2H read of the step's result
-        else:
-            out = run_step(b[:, 0], b[:, 1], None)      # numpy subs/rels: H2D inside model.forward
-            pinned_out.copy_(out, non_blocking=True)    # D2H of the (n, n_ent) score matrix
-            torch.cuda.current_stream().synchronize()
-    barrier()
-    t_e2e = time.perf_counter() - t0
 
-    times = torch.tensor([t_dev, t_e2e, float(edges_total), edge_ms, edge_bytes], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = times.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = times.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        t_dev, t_e2e = float(mx[0]), float(mx[1])
-        edges_all = float(sm[2])
-    else:
-        edges_all = float(edges_total)
+def allreduce_max_sum(B, values):
+    t = torch.tensor(values, dtype=torch.float64, device=B.dev)
+    if B.world > 1:
+        mx, sm = t.clone(), t.clone()
+        B.dist.all_reduce(mx, op=B.dist.ReduceOp.MAX)
+        B.dist.all_reduce(sm, op=B.dist.ReduceOp.SUM)
+        return mx.tolist(), sm.tolist()
+    return t.tolist(), t.tolist()
+
+
+def main():
+    args = parse_args()
+    guard_stdout()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    B = Bench(args)
+    world, rank = B.world, B.rank
+    args.gpus = world
+    gbps = lambda nbytes, ms: (nbytes / 1e9) / (ms * 1e-3) if ms > 0 else 0.0
+    peak = B.peak
+
+    head_batch = args.batch or (B.batch_train if args.train else B.batch_eval)
+    head = measure(B, args.train, head_batch, headline=True)
+    exp = measure_expand(B, B.mode(args.train), head_batch, head["first_batch"][0])
+    sub_train = None
+    if not args.train and not args.no_train_subsystem:
+        head["model"] = None                              # drop the eval model's captured graphs first
+        torch.cuda.empty_cache()
+        sub_train = measure(B, True, B.batch_train, headline=False)
+
+    (t_dev, t_e2e), _ = allreduce_max_sum(B, [head["t_dev"], head["t_e2e"]])
+    _, (edges_all,) = allreduce_max_sum(B, [float(head["edges_total"])])
+    if sub_train is not None:
+        (tt_dev,), _ = allreduce_max_sum(B, [sub_train["t_dev"]])
+        _, (tt_edges,) = allreduce_max_sum(B, [float(sub_train["edges_total"])])
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            B.dist.destroy_process_group()
         return
 
-    peak, peak_src = peaks()
-    traffic = None                                   # DRAM bytes per launch from the committed ncu capture
+    steps = args.steps
+    traffic, traffic_note = None, None                # DRAM bytes per launch from the committed ncu capture
     tpath = os.path.join(ROOT, "profiles", "edge_fwd_traffic.json")
     if os.path.isfile(tpath) and not args.train:
         with open(tpath) as f:
-            tj = json.load(f)
-        if tj.get("workload") == args.workload:
+            tj = json.load(f).get(args.workload)
+        if tj:
             traffic = tj["traffic_bytes_per_launch"]
-    qps = world * batch * args.steps / t_dev
-    gbps = lambda nbytes, ms: (nbytes / 1e9) / (ms * 1e-3) if ms > 0 else 0.0
-    achieved = gbps(edge_bytes, edge_ms)
+            traffic_note = tj.get("source")
+            if tj.get("kernel_build_id") != kernel_build_id():
+                traffic_note = "STALE: captured on rg_edge.cu build %s, this run is build %s; %s" % (
+                    tj.get("kernel_build_id"), kernel_build_id(), traffic_note)
+
+    def train_block(r, t, edges):
+        own = sum(v for k, v in r["kernel_ms"].items())
+        ms = 1e3 * t / steps
+        return {"step": "forward + backward + Adam" + (" + NCCL gradient all-reduce(SUM)" if world > 1 else ""),
+                "queries_per_gpu_per_step": r["batch"], "ms_per_step": ms,
+                "queries_per_s": world * r["batch"] * steps / t, "edges_per_s": edges / t,
+                "gpu_launches": int(r["launches"]),
+                "kernel_ms_per_step": {k: round(v, 4) for k, v in r["kernel_ms"].items()},
+                "own_kernel_share_of_step": own / ms if ms > 0 else None,
+                "edge_bwd": {"ms_per_step": r["bwd_ms"], "achieved": gbps(r["bwd_bytes"], r["bwd_ms"]), "peak": peak,
+                             "unit": "GB/s", "frac": gbps(r["bwd_bytes"], r["bwd_ms"]) / peak,
+                             "bytes_model": "(16+4d)*E + 8d*N per launch ((16+4d)*E at layer 0)"},
+                "edge_fwd": {"ms_per_step": r["edge_ms"], "achieved": gbps(r["edge_bytes"], r["edge_ms"]),
+                             "frac": gbps(r["edge_bytes"], r["edge_ms"]) / peak},
+                "allreduce": None if world == 1 else {"us_per_step": r["allreduce_us"], "bytes": r["grad_bytes"],
+                                                      "how": "one in-place NCCL all-reduce(SUM) of the flat gradient "
+                                                             "buffer (zero pack / unpack kernels), CUDA events"},
+                "dist_check": r.get("dist_check")}
+
+    cfg = config_of(args, B.data)
+    qps = world * head_batch * steps / t_dev
+    achieved = gbps(head["edge_bytes"], head["edge_ms"])
+    exp_ms, exp_emit_ms, exp_bytes, exp_edges = exp
     line = {
-        "metric": "queries/s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "metric": "queries/s", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": B.data,
         "edges_per_s": edges_all / t_dev,
-        "config": {"workload": workload_name(args.workload, n_layer) + (" + backward + Adam" if args.train else ""),
-                   "queries_per_gpu_per_step": batch, "hidden_dim": HIDDEN, "attn_dim": ATTN, "n_layer": n_layer,
-                   "edges_per_step_per_gpu": edges_total / args.steps,
-                   "l2": "flushed between timed steps (256 MiB write, untimed)", "parallelism": "dp%d" % world},
-        "e2e": {"value": world * batch * args.steps / t_e2e, "unit": "queries/s",
-                "h2d_bytes_per_step": int(batch * 16 + (batch * 8 if args.train else 0)),
-                "d2h_bytes_per_step": int(4 if args.train else batch * n_ent_out * 4)},
-        "gpu_launches": int(launches),
-        "kernel_ms_per_step": {k: round(v, 4) for k, v in kernel_ms.items()},
+        "config": cfg,
+        "run": {"edges_per_step_per_gpu": head["edges_total"] / steps,
+                "l2": "flushed between timed steps (256 MiB write, untimed)", "kernel_build_id": kernel_build_id()},
+        "e2e": {"value": world * head_batch * steps / t_e2e, "unit": "queries/s",
+                "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"]},
+        "gpu_launches": int(head["launches"]),
+        "kernel_ms_per_step": {k: round(v, 4) for k, v in head["kernel_ms"].items()},
         "roofline": {"bound": "hbm", "kernel": "k_edge_fwd (fused gather+attention+segmented reduce)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "share_of_step": t_instr / t_dev,
+                     "traffic": traffic, "traffic_source": traffic_note, "peak_source": B.peak_src,
+                     "share_of_step": head["edge_ms"] * 1e-3 * steps / head["t_dev"],
                      "timing": "CUDA events around every rg_edge_agg_fwd launch, instrumented pass over the same batches",
                      "bytes_model": "(16+4d)*E + 4d*N' per launch (16*E + 4d*N' at layer 0)"},
         "subsystems": {
             "expand": {"kernels": "rg_frontier_from_nodes + rg_frontier_step + rg_frontier_nodes + rg_frontier_remap "
-                                  "+ rg_edges_emit (explicit get_neighbors outputs, %d hops, one batch)" % n_layer,
-                       "ms": exp_ms, "ms_emit_part": exp_emit_ms, "edges": exp_edges, "achieved": gbps(exp_bytes, exp_ms), "peak": peak,
-                       "unit": "GB/s", "frac": gbps(exp_bytes, exp_ms) / peak,
+                                  "+ rg_edges_emit (explicit get_neighbors outputs, %d hops, one batch)" % B.n_layer,
+                       "ms": exp_ms, "ms_emit_part": exp_emit_ms, "edges": exp_edges, "achieved": gbps(exp_bytes, exp_ms),
+                       "peak": peak, "unit": "GB/s", "frac": gbps(exp_bytes, exp_ms) / peak,
                        "bytes_model": "56*E + 4*n_fact + 24*N + 16*N' per hop"},
-            "edge_fwd": {"ms_per_step": edge_ms, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "edge_fwd": {"ms_per_step": head["edge_ms"], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak},
-            "edge_bwd": None if not args.train else {
-                "ms_per_step": bwd_ms, "achieved": gbps(bwd_bytes, bwd_ms), "peak": peak,
-                "unit": "GB/s", "frac": gbps(bwd_bytes, bwd_ms) / peak,
-                "bytes_model": "(16+4d)*E + 8d*N per launch (16+4d)*E at layer 0"},
+            "train": train_block(head, t_dev, edges_all) if args.train else (
+                train_block(sub_train, tt_dev, tt_edges) if sub_train is not None else None),
         },
-        "clocks": clocks,
+        "clocks": head.get("clocks"),
     }
     if not args.no_cpu_baseline:
-        from oracle import redgnn_oracle as O
-        if inductive:
-            class _D(object):
-                pass
-            ind = O.InductiveData(task)
-            data = _D()
-            data.test_graph, data.test_q = ind.ind_graph, ind.test_q
-        elif task is None:
-            class _D(object):
-                pass
-            data = _D()
-            data.test_graph = O.Graph(loader._test_graph.triples, loader.n_ent, loader.n_rel)
-            data.test_q = loader.test_q
-        else:
-            data = O.TransductiveData(task)
-        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
+        ref = CpuReference(args.workload, B.task, B.inductive, B.n_layer, train=args.train)
         nq = max(1, args.cpu_queries)
-        q = np.array(data.test_q)
-        cpu_reference_step(O, data, sd, n_layer, q[:nq, 0], q[:nq, 1])           # warm-up
-        t0 = time.perf_counter()
-        reps, edges_cpu = 0, 0
-        while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 50):
-            b = q[(reps + 1) * nq:(reps + 2) * nq]
-            edges_cpu += cpu_reference_step(O, data, sd, n_layer, b[:, 0], b[:, 1])[1]
-            reps += 1
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": nq * reps / dt, "unit": "queries/s", "cores": cores, "kind": "port",
-                                "edges_per_s": edges_cpu / dt,
-                                "sample": "%d batches of %d queries of the same workload through the oracle port "
-                                          "(scipy SpGEMM + torch.unique + torch CPU), %.1f s" % (reps, nq, dt)}
+        reps, edges_cpu, dt = timed_cpu_sample(ref, nq, 10.0)
+        line["cpu_baseline"] = {"value": nq * reps / dt, "unit": "queries/s", "cores": cores, "kind": ref.kind,
+                                "edges_per_s": edges_cpu / dt, "queries_per_cpu_step": nq,
+                                "sample": "%d steps of %d queries of the same workload (of %d per GPU step), %.1f s; %s"
+                                          % (reps, nq, head_batch, dt, ref.describe())}
     emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

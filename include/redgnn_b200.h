@@ -137,6 +137,15 @@ int rg_graph_build(const int32_t *head, const int32_t *rel, const int32_t *tail,
                    int64_t n_fact, int32_t *in_ptr, int32_t *in_adj, int32_t *out_ptr, int32_t *out_adj,
                    void *ws, size_t ws_bytes, void *stream);
 
+/* shuffle_train (transductive/load_data.py:152-164) without the host round trip of the KG: `pool`
+ * [n_all][3] int32 is the fixed union of the fact and train triples (file order, device resident),
+ * `perm` the host-drawn np.random.permutation(n_all) (device int32; only its first n_keep = n_all*3/4
+ * entries are read).  Writes the new KG in reference row order: rows [0, n_keep) = pool[perm[i]],
+ * rows [n_keep, 2 n_keep) their inverses (t, r + n_rel, h) (double_triple :69-74), then the n_ent
+ * self-loops (e, 2 n_rel, e) (:77-79).  Follow with rg_graph_build on the same arrays. */
+int rg_graph_resplit(const int32_t *pool, const int32_t *perm, int64_t n_keep, int32_t n_ent,
+                     int32_t n_rel, int32_t *head, int32_t *rel, int32_t *tail, void *stream);
+
 /* ---- expansion: DataLoader.get_neighbors (transductive/load_data.py:106-131,
  *      inductive/load_data.py:115-143) --------------------------------------------------------- */
 
@@ -197,6 +206,12 @@ int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
                     float *node_small, float *g_rela, float *g_ar8, int32_t grad_copies,
                     const rg_heavy *heavy, void *stream);
 
+/* Which kernel variant rg_edge_agg_fwd / rg_edge_agg_bwd pick for these segments (pure host
+ * function, no launch; lets the parity tests assert that a shape exercises the path it is meant
+ * to): 0 = one warp per segment, 1 = eight segments per warp (short ones per 4-lane group),
+ * 2 = persistent CTAs with the relation tables staged in shared memory; negative rg_status. */
+int rg_edge_agg_variant(const rg_segments *seg, int32_t hidden_dim);
+
 /* ---- node update: models.py:41 (act(W_h agg)), :81 (h0 re-index), :83 (single-step nn.GRU, gate
  *      order r,z,n; dropout :82 is the identity in eval mode), next layer's Ws_attn(hidden) and
  *      :86 W_final(hidden).  Inference only (no saved state for autograd).
@@ -228,6 +243,15 @@ int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_row
                     const float *g_hidden, const float *saved, float *g_gi, float *g_gh, float *g_h0_direct,
                     float *bias_partial /* optional [ceil(n/64)][4][D]: per-CTA column sums of g_r, g_z, g_n, g_n*r */,
                     void *stream);
+
+/* Stale-row hygiene for shape-static training buffers (rows sized by an upper bound, true count on
+ * the device): zero rows [*n_now_dev, *n_prev_dev) of up to 8 row-major [rows][hidden_dim] float
+ * planes (`planes`: HOST array of device pointers), then *n_prev_dev = *n_now_dev.  After every step
+ * all rows past the true count are exact zeros, so a diverged step (NaN/Inf rows; the reference
+ * survives those by re-randomising NaN parameters, base_model.py:65-69) cannot poison the
+ * reductions over node rows of later steps. */
+int rg_zero_stale_rows(int32_t hidden_dim, const int64_t *n_now_dev, int64_t *n_prev_dev,
+                       float *const *planes, int32_t n_planes, void *stream);
 
 /* Glue of the graph-captured training step (all shape-static, true counts read on the device):
  *   rg_gather_scores: backward of rg_scatter_scores, g_node[j] = g_scores_all[b_j][e_j] (0 past n);

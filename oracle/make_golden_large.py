@@ -1,0 +1,107 @@
+"""Fixtures for the LARGE BASELINE shapes (configs[3], configs[4]) -- oracle outputs that take minutes
+of CPU time, computed once in the build container and committed, so the `-m gpu` tests compare
+the CUDA path against them without re-running the CPU oracle on the GPU box:
+
+    python oracle/make_golden_large.py [yago310] [plscaled] [powerlaw]
+
+TEST INFRASTRUCTURE ONLY.  The graphs are NOT stored: they are regenerated from the seeded, numpy-only
+generator `kg_synth` (same image on both boxes => same arrays; a SHA-256 of the test-graph triples is
+stored and checked by the tests).  The producer is `oracle/redgnn_oracle.py`, itself pinned against the
+live reference (tests/test_oracle_vs_reference.py).
+
+  yago310   YAGO3-10-shaped (123,182 entities, 37 relations, 1,079,040 triples), n_layer 5: eval scores of 2 queries
+  plscaled  power-law-shaped at 1/10 scale (100 k entities, 500 relations, 1 M triples), n_layer 6: eval scores of 2
+            queries + every parameter gradient of the training loss of 2 train triples (fp64, and the max
+            error the oracle's own fp32 evaluation makes against it)
+  powerlaw  full size (1 M entities, 500 relations, 10 M triples), n_layer 6: ONE query; 131,072 sampled
+            entity scores + the bit-packed visited mask
+"""
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import kg_synth  # noqa: E402
+from oracle import redgnn_oracle as O  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+PLSCALED = (100000, 500, 1000000, 500, 500, 1.0, 1.0, 6)
+
+
+def tri_sha(tri):
+    return hashlib.sha256(np.ascontiguousarray(tri.astype(np.int64)).tobytes()).hexdigest()
+
+
+def eval_block(sp, n_layer, n_q, seed=1234):
+    g = O.Graph(sp.test_graph_triples, sp.n_ent, sp.n_rel)
+    sd = O.init_state_dict(n_layer, 48, 5, sp.n_rel, seed=seed)
+    q = np.array(sp.test_q)[:n_q]
+    with torch.no_grad():
+        scores, trace = O.model_forward(sd, g, q[:, 0], q[:, 1], n_layer, "relu", return_trace=True)
+    return sd, q, scores, [int(t[1].shape[0]) for t in trace]
+
+
+def yago310():
+    t0 = time.time()
+    sp = kg_synth.ArraySplits("yago310", seed=0)
+    sd, q, scores, edges = eval_block(sp, 5, 2)
+    fx = {"graph_sha": np.array(tri_sha(sp.test_graph_triples)), "queries": q.astype(np.int64),
+          "scores": scores.numpy().astype(np.float32), "edges": np.array(edges, dtype=np.int64),
+          "seed": np.int64(1234)}
+    np.savez_compressed(os.path.join(OUT, "yago310.npz"), **fx)
+    print("yago310 edges", edges, "%.0f s" % (time.time() - t0), flush=True)
+
+
+def plscaled():
+    t0 = time.time()
+    sp = kg_synth.ArraySplits(override=PLSCALED, seed=0)
+    sd, q, scores, edges = eval_block(sp, 6, 2)
+    fx = {"graph_sha": np.array(tri_sha(sp.test_graph_triples)), "queries": q.astype(np.int64),
+          "scores": scores.numpy().astype(np.float32), "edges": np.array(edges, dtype=np.int64),
+          "seed": np.int64(1234)}
+    print("plscaled eval edges", edges, "%.0f s" % (time.time() - t0), flush=True)
+    # training-loss gradients on the TRAIN graph (base_model.py:56-61), 2 train triples
+    g = O.Graph(sp.train_graph_triples, sp.n_ent, sp.n_rel)
+    tri = sp.train_data[:2]
+    grads = []
+    for conv in ((lambda t: t.clone()), (lambda t: t.double())):
+        sd_g = {k: conv(v).requires_grad_(True) for k, v in sd.items()}
+        loss = O.train_loss(O.model_forward(sd_g, g, tri[:, 0], tri[:, 1], 6, "relu"), tri[:, 2])
+        loss.backward()
+        grads.append(({k: v.grad for k, v in sd_g.items()}, float(loss.detach())))
+        print("plscaled grads pass done %.0f s" % (time.time() - t0), flush=True)
+    (g32, l32), (g64, l64) = grads
+    fx["train_triples"] = tri.astype(np.int64)
+    fx["train_graph_sha"] = np.array(tri_sha(sp.train_graph_triples))
+    fx["loss64"], fx["loss32"] = np.float64(l64), np.float64(l32)
+    for k in g64:
+        fx["g64." + k] = g64[k].numpy()
+        fx["err32." + k] = np.float64((g32[k].double() - g64[k]).abs().max())
+    np.savez_compressed(os.path.join(OUT, "plscaled.npz"), **fx)
+    print("plscaled done %.0f s" % (time.time() - t0), flush=True)
+
+
+def powerlaw():
+    t0 = time.time()
+    sp = kg_synth.ArraySplits("powerlaw", seed=0)
+    sd, q, scores, edges = eval_block(sp, 6, 1)
+    s = scores.numpy().astype(np.float32)[0]
+    idx = np.sort(np.random.default_rng(5).choice(sp.n_ent, 131072, replace=False))
+    fx = {"graph_sha": np.array(tri_sha(sp.test_graph_triples)), "queries": q.astype(np.int64),
+          "sample_idx": idx.astype(np.int32), "sample_scores": s[idx], "visited_bits": np.packbits(s != 0),
+          "score_absmax": np.float64(np.abs(s).max()), "edges": np.array(edges, dtype=np.int64), "seed": np.int64(1234)}
+    np.savez_compressed(os.path.join(OUT, "powerlaw_1q.npz"), **fx)
+    print("powerlaw edges", edges, "%.0f s" % (time.time() - t0), flush=True)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    which = sys.argv[1:] or ["yago310", "plscaled", "powerlaw"]
+    for name in which:
+        {"yago310": yago310, "plscaled": plscaled, "powerlaw": powerlaw}[name]()

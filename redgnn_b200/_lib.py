@@ -50,6 +50,7 @@ SIGNATURES = {
     "rg_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
     "rg_graph_build_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
     "rg_graph_build": (C.c_int, [C.c_void_p] * 3 + [C.c_int32, C.c_int64] + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
+    "rg_graph_resplit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 4),
     "rg_frontier_from_nodes": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(RgFrontier), C.c_void_p,
                                          C.c_void_p, C.c_size_t, C.c_void_p]),
     "rg_frontier_step": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64, C.c_int64] + [C.c_void_p] * 8),
     "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
     "rg_scatter_rows": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
+    "rg_zero_stale_rows": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "rg_query_sum8": (C.c_int, [C.c_int32] + [C.c_void_p] * 4),
     "rg_filtered_ranks": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 7),
     "rg_scatter_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
@@ -69,6 +71,7 @@ SIGNATURES = {
                                 C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p]),
     "rg_edge_agg_fwd": (C.c_int, [C.POINTER(RgSegments), C.c_int32] + [C.c_void_p] * 8
                         + [C.POINTER(RgHeavy), C.c_void_p]),
+    "rg_edge_agg_variant": (C.c_int, [C.POINTER(RgSegments), C.c_int32]),
     "rg_edge_agg_bwd": (C.c_int, [C.POINTER(RgSegments), C.c_int32] + [C.c_void_p] * 12
                         + [C.c_int32, C.POINTER(RgHeavy), C.c_void_p]),
 }

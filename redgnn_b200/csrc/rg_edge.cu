@@ -906,6 +906,13 @@ constexpr int kHeavyGrid = 148 * 4;
 // 8 segments per warp only pays when that still leaves every SM several blocks of warps
 constexpr int64_t kBlock8MinSegs = 8 * 148 * 64;
 
+// 0 = one warp per segment, 1 = eight segments per warp, 2 = persistent + shared-memory tables
+inline int pick_variant(const rg_segments *seg, int D) {
+    const size_t tab_bytes = (size_t)seg->n_table_rows * (D + 8) * sizeof(float);
+    if (seg->mode == 1 && seg->n_table_rows > 0 && tab_bytes <= 110 * 1024 && seg->n_seg >= 4096) return 2;
+    return seg->n_seg >= kBlock8MinSegs ? 1 : 0;
+}
+
 template <int D, bool HH, bool IM>
 int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, const float *rela, const float *ar8,
                const float *aq8, const float *w8, const float *b_alpha, float *agg, const rg_heavy *heavy,
@@ -918,7 +925,7 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
     bool persistent = false;
     if constexpr (IM) {
         // relation tables staged in shared memory when two 16-warp CTAs still fit one SM
-        if (seg->n_table_rows > 0 && tab_bytes <= 110 * 1024 && seg->n_seg >= 4096) {
+        if (pick_variant(seg, D) == 2) {
             auto kern = k_edge_fwd_p<D, HH>;
             RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
             int dev = 0, n_sm = 148, per_sm = 1;
@@ -967,7 +974,7 @@ int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, co
     const size_t tab_bytes = (size_t)seg->n_table_rows * (D + 8) * sizeof(float);
     bool persistent = false;
     if constexpr (IM) {
-        if (seg->n_table_rows > 0 && tab_bytes <= 110 * 1024 && seg->n_seg >= 4096) {
+        if (pick_variant(seg, D) == 2) {
             auto kern = k_edge_bwd_p<D, HH>;
             RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
             int dev = 0, n_sm = 148, per_sm = 1;
@@ -1067,6 +1074,13 @@ int rg_edge_agg_bwd(const rg_segments *seg, int32_t hidden_dim, const float *hid
     else { RG_BWD(false, false); }
 #undef RG_BWD
     return rc;
+}
+
+int rg_edge_agg_variant(const rg_segments *seg, int32_t hidden_dim) {
+    int rc = check_segments(seg);
+    if (rc) return rc;
+    if (hidden_dim != 16 && hidden_dim != 32 && hidden_dim != 48 && hidden_dim != 64) return RG_ERR_UNSUPPORTED;
+    return pick_variant(seg, hidden_dim);
 }
 
 }  // extern "C"

@@ -69,7 +69,33 @@ int build_csr(int64_t F, int32_t n_ent, const int32_t *key, const int32_t *other
     return RG_OK;
 }
 
+// shuffle_train on the device: permuted pool rows -> fact rows, their inverses, self-loops
+__global__ void k_resplit(const int32_t *__restrict__ pool, const int32_t *__restrict__ perm, int64_t n_keep,
+                          int32_t n_ent, int32_t n_rel, int32_t *head, int32_t *rel, int32_t *tail) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n_keep) {
+        const int64_t src = perm[i];
+        const int h = pool[3 * src], r = pool[3 * src + 1], t = pool[3 * src + 2];
+        head[i] = h, rel[i] = r, tail[i] = t;
+        head[n_keep + i] = t, rel[n_keep + i] = r + n_rel, tail[n_keep + i] = h;
+    } else if (i < n_keep + n_ent) {
+        const int e = (int)(i - n_keep);
+        const int64_t row = 2 * n_keep + e;
+        head[row] = e, rel[row] = 2 * n_rel, tail[row] = e;
+    }
+}
+
 }  // namespace
+
+extern "C" int rg_graph_resplit(const int32_t *pool, const int32_t *perm, int64_t n_keep, int32_t n_ent,
+                                int32_t n_rel, int32_t *head, int32_t *rel, int32_t *tail, void *stream) {
+    if (!pool || !perm || n_keep < 0 || n_ent <= 0 || n_rel <= 0 || !head || !rel || !tail) return RG_ERR_BAD_ARG;
+    if (2 * n_keep + n_ent >= (int64_t)INT32_MAX) return RG_ERR_TOO_LARGE;
+    k_resplit<<<(unsigned)rg_cdiv(n_keep + n_ent, 256), 256, 0, (cudaStream_t)stream>>>(pool, perm, n_keep, n_ent,
+                                                                                        n_rel, head, rel, tail);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
 
 extern "C" size_t rg_graph_build_workspace_bytes(int32_t n_ent, int64_t n_fact) {
     if (n_ent <= 0 || n_fact <= 0) return 0;

@@ -79,13 +79,19 @@ def _cached_query_array(obj, name):
 
 
 class _GraphSlot(object):
-    """Host triples of one KG + its lazily built device copy."""
+    """Host triples of one KG (or a thunk producing them) + its lazily built device copy."""
 
-    def __init__(self, triples, n_ent, n_rel):
-        self.triples = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+    def __init__(self, triples, n_ent, n_rel, n_triples=None):
+        self._triples = triples if callable(triples) else np.asarray(triples, dtype=np.int64).reshape(-1, 3)
         self.n_ent, self.n_rel = n_ent, n_rel
-        self.n_fact = len(self.triples) + n_ent
+        self.n_fact = (n_triples if n_triples is not None else len(self._triples)) + n_ent
         self._dev = {}
+
+    @property
+    def triples(self):
+        if callable(self._triples):
+            self._triples = np.asarray(self._triples(), dtype=np.int64).reshape(-1, 3)
+        return self._triples
 
     def on(self, device):
         key = str(device)
@@ -94,6 +100,16 @@ class _GraphSlot(object):
             g = DeviceGraph(self.triples, self.n_ent, self.n_rel, device)
             self._dev = {key: g}
         return g
+
+    def device_graph(self):
+        """The device copy if one has been built (any device), else None."""
+        return next(iter(self._dev.values()), None)
+
+    def adopt(self, other):
+        """Take over `other`'s device copy after it was rebuilt IN PLACE with this slot's triples:
+        the DeviceGraph object (and every device address captured CUDA graphs hold) stays the same."""
+        self._dev = other._dev
+        other._dev = {}
 
     def kg(self):
         """The reference's KG array ([triples ; self-loops]) as int64."""
@@ -156,8 +172,15 @@ class TransductiveLoader(object):
         return np.concatenate([a, inv], axis=0)
 
     def load_graph(self, triples):
+        """load_data.py:76-81.  A re-load of the same size (shuffle_train, every epoch) rebuilds the device
+        copy in place, so CUDA graphs captured on the train KG survive the epoch boundary."""
+        old = getattr(self, '_train_graph', None)
         self._train_graph = _GraphSlot(triples, self.n_ent, self.n_rel)
         self.n_fact = self._train_graph.n_fact
+        g = old.device_graph() if old is not None else None
+        if g is not None and g.device.type == 'cuda' and g.n_fact == self.n_fact:
+            g.rebuild(self._train_graph.triples)
+            self._train_graph.adopt(old)
 
     def load_test_graph(self, triples):
         self._test_graph = _GraphSlot(triples, self.n_ent, self.n_rel)
@@ -196,14 +219,43 @@ class TransductiveLoader(object):
         return _cached_query_array(self, name)
 
     def shuffle_train(self):
-        """load_data.py:152-164: re-split facts+train 3:1 with np.random and rebuild the graph."""
-        all_triple = np.concatenate([np.array(self.fact_triple), np.array(self.train_triple)], axis=0)
-        n_all = len(all_triple)
-        all_triple = all_triple[np.random.permutation(n_all)]
-        self.fact_data = self.double_triple(all_triple[:n_all * 3 // 4])
-        self.train_data = self.double_triple(all_triple[n_all * 3 // 4:])
+        """load_data.py:152-164: re-split facts+train 3:1 with np.random (same stream, same permutation
+        as the reference) and rebuild the graph.  With the train KG on a GPU the re-split itself runs
+        there (rg_graph_resplit on the resident fact+train pool, then rg_graph_build, both in place):
+        only the 4-byte-per-triple permutation crosses PCIe, and the host keeps just the quarter that
+        becomes `train_data`; `fact_data` / `KG` are materialised lazily if someone asks."""
+        pool = self.__dict__.get('_pool')
+        if pool is None:
+            pool = self._pool = np.concatenate([np.array(self.fact_triple, dtype=np.int64).reshape(-1, 3),
+                                                np.array(self.train_triple, dtype=np.int64).reshape(-1, 3)], axis=0)
+        n_all = len(pool)
+        rand_idx = np.random.permutation(n_all)
+        n_keep = n_all * 3 // 4
+        self.train_data = self.double_triple(pool[rand_idx[n_keep:]])
         self.n_train = len(self.train_data)
-        self.load_graph(self.fact_data)
+        g = self._train_graph.device_graph()
+        if g is None or g.device.type != 'cuda' or 2 * n_keep + self.n_ent != g.n_fact:
+            self.fact_data = self.double_triple(pool[rand_idx[:n_keep]])
+            self.load_graph(self.fact_data)
+            return
+        pool_dev = self.__dict__.get('_pool_dev')
+        if pool_dev is None or pool_dev.device != g.device:
+            pool_dev = self._pool_dev = torch.as_tensor(pool.astype(np.int32)).to(g.device)
+        perm_dev = torch.as_tensor(rand_idx[:n_keep].astype(np.int32)).to(g.device, non_blocking=True)
+        g.resplit(pool_dev, perm_dev, n_keep)
+        keep = rand_idx[:n_keep]
+        slot = _GraphSlot(lambda: self.double_triple(pool[keep]), self.n_ent, self.n_rel, n_triples=2 * n_keep)
+        slot.adopt(self._train_graph)
+        self._train_graph = slot
+        self.n_fact = slot.n_fact
+        self.__dict__.pop('fact_data', None)          # stale; the property below rebuilds it on demand
+
+    def __getattr__(self, name):
+        if name == 'fact_data':                       # only reached when the attribute is not set
+            tg = self.__dict__.get('_train_graph')
+            if tg is not None:
+                return tg.triples
+        raise AttributeError(name)
 
 
 class InductiveLoader(object):

@@ -51,6 +51,23 @@ def allreduce_gradients(parameters, group=None):
     return flat.numel()
 
 
+def allreduce_flat(flat, group=None):
+    """All-reduce(SUM) of an already-flat gradient buffer in place (RedGNN.flat_grad() with
+    `grads_in_place`: the parameters' .grad are views of it, so there is nothing to pack or unpack)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat.numel()
+
+
+def allreduce_model_gradients(model, group=None):
+    """The gradient exchange of one training step: the flat in-place buffer when the model provides
+    one, else the pack / all-reduce / unpack path over the parameters."""
+    flat = model.flat_grad() if hasattr(model, "flat_grad") else None
+    if flat is not None:
+        return allreduce_flat(flat, group)
+    return allreduce_gradients(model.parameters(), group)
+
+
 def broadcast_parameters(module, src=0, group=None):
     """Make every rank start from rank `src`'s weights (after that identical SUM-reduced gradients
     and identical optimiser steps keep them in sync without further broadcasts)."""
@@ -74,9 +91,12 @@ def sharded_train_step(model, optimizer, triples, rank=None, world=None, group=N
         mx = scores.max(1, keepdim=True)[0]
         loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(scores - mx), 1)))
         loss.backward()
+        allreduce_model_gradients(model, group)
     else:
+        # empty shard: contribute zeros with the same message layout (the flat in-place buffer would
+        # still hold the previous step's gradients)
         loss = torch.zeros((), device=next(model.parameters()).device)
-    allreduce_gradients(model.parameters(), group)
+        allreduce_gradients(model.parameters(), group)
     optimizer.step()
     return loss.detach()
 

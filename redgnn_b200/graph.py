@@ -30,7 +30,9 @@ class DeviceGraph(object):
     def __init__(self, triples, n_ent, n_rel, device):
         """triples: int array [T,3] (h, r, t) WITHOUT the self-loop block (it is appended here,
         exactly like load_graph, load_data.py:76-81)."""
-        tri = torch.as_tensor(np.asarray(triples, dtype=np.int64).reshape(-1, 3))
+        tri_np = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+        self._validate(tri_np, n_ent, n_rel)
+        tri = torch.as_tensor(tri_np)
         ids = torch.arange(n_ent, dtype=torch.int64)
         loops = torch.stack([ids, torch.full_like(ids, 2 * n_rel), ids], dim=1)
         kg = torch.cat([tri, loops], dim=0).to(device)
@@ -38,30 +40,89 @@ class DeviceGraph(object):
         self.n_ent, self.n_rel, self.n_fact = int(n_ent), int(n_rel), int(kg.shape[0])
         h, r, t = kg[:, 0].contiguous(), kg[:, 1].contiguous(), kg[:, 2].contiguous()
         self.head, self.rel, self.tail = (x.to(torch.int32).contiguous() for x in (h, r, t))
+        self.heavy_in, self.heavy_out = (0, 0), (0, 0)
+        self.epoch = 0            # bumped when an in-place rebuild outgrows the heavy-queue bounds (see rebuild)
+        self._ws_cur = None
+        self._build_ws = None
+        self._c = None
         if self.device.type == 'cuda':
             # device build through the C ABI (stable radix sort of the fact ids by tail / by head)
             i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=self.device)
             self.in_ptr, self.in_adj = i32(n_ent + 1), i32(self.n_fact, 2)
             self.out_ptr, self.out_adj = i32(n_ent + 1), i32(self.n_fact, 2)
-            with torch.cuda.device(self.device):
-                ws = torch.empty(lib.rg_graph_build_workspace_bytes(n_ent, self.n_fact), dtype=torch.uint8,
-                                 device=self.device)
-                check(lib.rg_graph_build(ptr(self.head), ptr(self.rel), ptr(self.tail), n_ent, self.n_fact,
-                                         ptr(self.in_ptr), ptr(self.in_adj), ptr(self.out_ptr), ptr(self.out_adj),
-                                         ptr(ws), ws.numel(), stream_ptr()))
-            in_deg = (self.in_ptr[1:] - self.in_ptr[:-1]).long()
-            out_deg = (self.out_ptr[1:] - self.out_ptr[:-1]).long()
+            self._build_csr(grow_only=False)
         else:
             # host-side construction of the same arrays (data preparation only; used by the CPU tests of
             # the loaders -- every kernel entry point still requires CUDA tensors)
             self.in_ptr, self.in_adj, in_deg = _csr(t, h, r, n_ent)
             self.out_ptr, self.out_adj, out_deg = _csr(h, t, r, n_ent)
+            self._set_heavy(in_deg, out_deg, False)
+
+    @staticmethod
+    def _validate(tri, n_ent, n_rel):
+        """The kernels index by these ids without bounds checks (the reference fails in scipy's
+        csr_matrix on such input, load_data.py:80): refuse them here."""
+        if len(tri) == 0:
+            return
+        if tri[:, [0, 2]].min() < 0 or tri[:, [0, 2]].max() >= n_ent:
+            raise _lib.RgError("DeviceGraph: entity id outside [0, %d)" % n_ent)
+        if tri[:, 1].min() < 0 or tri[:, 1].max() > 2 * n_rel:
+            raise _lib.RgError("DeviceGraph: relation id outside [0, %d]" % (2 * n_rel))
+
+    def _build_csr(self, grow_only):
+        with torch.cuda.device(self.device):
+            if self._build_ws is None:
+                self._build_ws = torch.empty(lib.rg_graph_build_workspace_bytes(self.n_ent, self.n_fact),
+                                             dtype=torch.uint8, device=self.device)
+            ws = self._build_ws
+            check(lib.rg_graph_build(ptr(self.head), ptr(self.rel), ptr(self.tail), self.n_ent, self.n_fact,
+                                     ptr(self.in_ptr), ptr(self.in_adj), ptr(self.out_ptr), ptr(self.out_adj),
+                                     ptr(ws), ws.numel(), stream_ptr()))
+        if not grow_only:
+            self._build_ws = None        # first build: the sort scratch (~20 B/fact) is kept only once rebuilds start
+        in_deg = (self.in_ptr[1:] - self.in_ptr[:-1]).long()
+        out_deg = (self.out_ptr[1:] - self.out_ptr[:-1]).long()
+        self._set_heavy(in_deg, out_deg, grow_only)
+
+    def _set_heavy(self, in_deg, out_deg, grow_only):
+        """Per-query upper bounds (chunks, nodes) for the heavy-segment queues of the edge kernels.
+        Captured CUDA graphs have queue buffers of these sizes baked in, so an in-place rebuild only
+        ever GROWS them (with 10 % headroom) and bumps `epoch`, which is part of the capture keys."""
         ck = _lib.RG_HEAVY_CHUNK
-        # per-query upper bounds for the heavy-segment queues of the edge kernels
-        self.heavy_in = (int(((in_deg - 1) // ck).sum()), int((in_deg > ck).sum()))
-        self.heavy_out = (int(((out_deg - 1) // ck).sum()), int((out_deg > ck).sum()))
-        self._ws = {}
-        self._c = None
+        stats = torch.stack([((in_deg - 1) // ck).sum(), (in_deg > ck).sum(),
+                             ((out_deg - 1) // ck).sum(), (out_deg > ck).sum()]).cpu().tolist()
+        exact_in, exact_out = (int(stats[0]), int(stats[1])), (int(stats[2]), int(stats[3]))
+        if not grow_only:
+            self.heavy_in, self.heavy_out = exact_in, exact_out
+            return
+        fits = all(a <= b for a, b in zip(exact_in + exact_out, self.heavy_in + self.heavy_out))
+        if not fits:
+            grow = lambda new, old: tuple(max(o, n + n // 10 + 1) if n > o else o for n, o in zip(new, old))
+            self.heavy_in, self.heavy_out = grow(exact_in, self.heavy_in), grow(exact_out, self.heavy_out)
+            self.epoch += 1
+
+    def rebuild(self, triples):
+        """Same-size KG in place (shuffle_train re-splits keep the row count): all device addresses
+        stay valid, so CUDA graphs captured on this KG keep working."""
+        tri = np.asarray(triples, dtype=np.int64).reshape(-1, 3)
+        if len(tri) + self.n_ent != self.n_fact or self.device.type != 'cuda':
+            raise _lib.RgError("DeviceGraph.rebuild needs a CUDA graph and the same number of triples")
+        self._validate(tri, self.n_ent, self.n_rel)
+        dev = torch.as_tensor(tri.astype(np.int32)).to(self.device, non_blocking=True)
+        n = len(tri)
+        self.head[:n].copy_(dev[:, 0])
+        self.rel[:n].copy_(dev[:, 1])
+        self.tail[:n].copy_(dev[:, 2])
+        self._build_csr(grow_only=True)
+
+    def resplit(self, pool_dev, perm_dev, n_keep):
+        """shuffle_train on the device (rg_graph_resplit + rg_graph_build), in place."""
+        if 2 * n_keep + self.n_ent != self.n_fact:
+            raise _lib.RgError("DeviceGraph.resplit: row count changes (%d -> %d)" % (self.n_fact, 2 * n_keep + self.n_ent))
+        with torch.cuda.device(self.device):
+            check(lib.rg_graph_resplit(ptr(pool_dev), ptr(perm_dev), n_keep, self.n_ent, self.n_rel, ptr(self.head),
+                                       ptr(self.rel), ptr(self.tail), stream_ptr()))
+        self._build_csr(grow_only=True)
 
     # ---- ctypes views -------------------------------------------------------------------
     def c_struct(self):
@@ -75,13 +136,14 @@ class DeviceGraph(object):
         return torch.stack([self.head, self.rel, self.tail], 1).cpu().numpy().astype(np.int64)
 
     def workspace(self, n_query):
-        ws = self._ws.get(n_query)
-        if ws is None:
-            nbytes = lib.rg_workspace_bytes(n_query, self.n_ent, self.n_fact)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            if len(self._ws) > 8:
-                self._ws.clear()
-            self._ws[n_query] = ws
+        """Scratch for the scans of one expansion call chain.  One buffer, grown on demand and never
+        freed while something may still point at it: captured CUDA graphs have its address baked in,
+        so whoever captures keeps a reference to the tensor returned here (RedGNN._run_graph,
+        TrainStepRunner); replacing `_ws_cur` with a larger buffer then leaves theirs alive."""
+        nbytes = lib.rg_workspace_bytes(n_query, self.n_ent, self.n_fact)
+        ws = self._ws_cur
+        if ws is None or ws.numel() < nbytes:
+            ws = self._ws_cur = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         return ws
 
     # ---- frontier API ---------------------------------------------------------------------

@@ -126,7 +126,12 @@ class RedGNN(torch.nn.Module):
         device-side hop counts, i.e. synchronises, on first access)."""
         st = self._last_stats
         if isinstance(st, list):
-            counts = torch.stack([fr.counts for fr in st]).cpu()
+            fr0 = getattr(st[0], "source_frontier", None)       # frontier of the query subjects: holds RG_CNT_ERR
+            counts = torch.stack([fr.counts for fr in st] + ([fr0.counts] if fr0 is not None else [])).cpu()
+            if fr0 is not None:
+                if int(counts[-1][_lib.RG_CNT_ERR]):
+                    raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % fr0.n_ent)
+                counts = counts[:-1]
             for fr, c in zip(st, counts):
                 fr.n_nodes = int(c[_lib.RG_CNT_N_OUT])
                 fr.n_edges = int(c[_lib.RG_CNT_E])
@@ -138,13 +143,14 @@ class RedGNN(torch.nn.Module):
     # once into a CUDA graph and replayed: the ~100 launches / allocations of a forward cost one
     # cudaGraphLaunch instead of milliseconds of host time.
     use_cuda_graph = True
+    check_tensor_inputs = True         # False: sync-free serving; range errors then surface in `last_stats`
     inference_in_eval = True
     fused_train_node_update = True     # autograd path: node update in the tcgen05 kernel (hidden_dim <= 48)
     MAX_CACHED_GRAPHS = 4
 
     def _run_graph(self, q_sub, q_rel, graph, n_ent_out):
         n = q_sub.shape[0]
-        key = (n, id(graph), n_ent_out, tuple(p.data_ptr() for p in self.parameters()))
+        key = (n, id(graph), graph.epoch, n_ent_out, tuple(p.data_ptr() for p in self.parameters()))
         cache = self.__dict__.setdefault("_graph_cache", {})
         entry = cache.get(key)
         if entry is None:
@@ -159,8 +165,9 @@ class RedGNN(torch.nn.Module):
             cg = torch.cuda.CUDAGraph()
             with torch.cuda.graph(cg):
                 out = self._run_async(sub_buf, rel_buf, graph, n_ent_out)
+            # "kg" / "ws": the captured launches have the KG arrays' and the expansion scratch's addresses baked in
             entry = {"graph": cg, "sub": sub_buf, "rel": rel_buf, "out": out, "frontiers": self._last_stats,
-                     "launches": _lib.Stats.launches - before, "kg": graph}
+                     "launches": _lib.Stats.launches - before, "kg": graph, "ws": graph.workspace(n)}
             _lib.Stats.launches = before
             while len(cache) >= self.MAX_CACHED_GRAPHS:
                 cache.pop(next(iter(cache)))
@@ -175,15 +182,19 @@ class RedGNN(torch.nn.Module):
     # Training: forward and hand-written backward of the whole path captured as two CUDA graphs
     # (train_graph.py); the eager autograd path below remains for hidden_dim 64 / profiling.
     graph_train = True
+    grads_in_place = False             # see train_graph.TrainStepFunction
     MAX_CACHED_TRAIN_GRAPHS = 2
 
     def _run_train_graph(self, q_sub, q_rel, graph, n_ent_out):
         from .train_graph import TrainStepRunner, TrainStepFunction
         p_drop = float(self.dropout.p) if self.training else 0.0
-        key = (q_sub.shape[0], id(graph), n_ent_out, p_drop, tuple(p.data_ptr() for p in self.parameters()))
+        key = (q_sub.shape[0], id(graph), graph.epoch, n_ent_out, p_drop,
+               tuple(p.data_ptr() for p in self.parameters()))
         cache = self.__dict__.setdefault("_train_graph_cache", {})
         runner = cache.get(key)
         if runner is None:
+            for k in [k for k, r in cache.items() if r.graph is graph and r.kg_epoch != graph.epoch]:
+                cache.pop(k)                     # runners whose heavy-queue bounds the rebuilt KG outgrew
             while len(cache) >= self.MAX_CACHED_TRAIN_GRAPHS:
                 cache.pop(next(iter(cache)))
             saved_p, self.dropout.p = self.dropout.p, p_drop
@@ -194,7 +205,14 @@ class RedGNN(torch.nn.Module):
             cache[key] = runner
         scores = TrainStepFunction.apply(runner, q_sub, q_rel, *[runner.params[k] for k in runner.names])
         self._last_stats = runner.frontiers
+        self._last_runner = runner
         return scores
+
+    def flat_grad(self):
+        """With `grads_in_place`: the flat gradient buffer of the latest graph-captured training step
+        (every parameter's .grad is a view of it, in named_parameters() order), else None."""
+        r = self.__dict__.get("_last_runner")
+        return r.flat_grad if r is not None and self.grads_in_place else None
 
     def _run_async(self, q_sub, q_rel, graph, n_ent_out):
         """Inference without ANY host synchronisation: every per-layer buffer is sized by the upper
@@ -227,6 +245,8 @@ class RedGNN(torch.nn.Module):
             hidden, as8, scores = node_update(agg, hidden, src, layer.W_h.weight, self.gate,
                                               ACT_CODES[self.act_name], ws_next,
                                               self.W_final.weight if last else None, n_dev=n_dev)
+            if i == 0:
+                fr_next.source_frontier = fr
             frontiers.append(fr_next)
             fr = fr_next
         self._last_stats = frontiers                      # resolved lazily by `last_stats`
@@ -243,6 +263,7 @@ class RedGNN(torch.nn.Module):
             return self._run_on_device(subs, rels, graph, n_ent_out, dev)
 
     def _run_on_device(self, subs, rels, graph, n_ent_out, dev):
+        self._last_runner = None           # set again by the graph-captured training path only
         n = len(subs)
         d = self.hidden_dim
         if not isinstance(subs, torch.Tensor):
@@ -250,6 +271,13 @@ class RedGNN(torch.nn.Module):
             if len(s) and (s.min() < 0 or s.max() >= graph.n_ent):
                 raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % graph.n_ent)
         q_sub, q_rel = self._to_device(subs, dev), self._to_device(rels, dev)
+        if isinstance(subs, torch.Tensor) and self.check_tensor_inputs and n > 0:
+            # the kernels drop an out-of-range (query, entity) silently (all-zero scores): one 2-scalar
+            # read-back keeps the eager path's error behaviour for tensor inputs too
+            lo, hi = torch.aminmax(q_sub)
+            lo, hi = torch.stack([lo, hi]).tolist()
+            if lo < 0 or hi >= graph.n_ent:
+                raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % graph.n_ent)
         # eval(): the reference's evaluate() never differentiates (base_model.py:106 takes .data), so an
         # eval-mode forward runs the inference kernels and returns a tensor WITHOUT autograd history
         # unless `inference_in_eval` is switched off; train() mode always keeps autograd.

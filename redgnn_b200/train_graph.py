@@ -9,10 +9,13 @@ backward, GRU elementwise kernel + library GEMMs, small projection GEMMs), and b
 once as CUDA graphs.  A single torch.autograd.Function replays them, so `loss.backward()` and the
 optimiser in the caller's loop (Static/*/base_model.py:49-70) work unchanged.
 
-Invariant that makes upper-bound buffers safe: every persistent buffer starts as zeros and only ever
-holds finite values, and every gradient row past the true node count is an exact zero
-(rg_gru_bwd_elem / rg_gather_scores write zeros there, node_small is cleared per replay), so stale
-rows only ever meet zeros in the reductions over nodes.
+Invariant that makes upper-bound buffers safe: after every forward replay each persistent per-node
+buffer (agg, hidden, the saved gate planes) is an exact zero in every row past that step's true node
+count -- the buffers start as zeros, the kernels write rows below the count only, and
+rg_zero_stale_rows clears the rows a larger previous step left behind (so even a diverged step,
+which the reference loop survives by re-randomising NaN parameters, base_model.py:65-69, cannot leak
+NaN/Inf into later steps); every gradient row past the true count is an exact zero as well
+(rg_gru_bwd_elem / rg_gather_scores write zeros there, node_small is cleared per replay).
 
 The forward always runs on the full upper-bound buffers.  The backward is dominated by dense GEMMs
 over node rows that cannot stop at a device-side count, and the early layers hold far fewer nodes
@@ -78,6 +81,9 @@ class TrainStepRunner(object):
         self.agg = [z(self.cap, self.d) for _ in range(self.n_layer)]
         self.hidden = [z(self.cap, self.d) for _ in range(self.n_layer)]
         self.saved = [z(6, self.cap, self.d) for _ in range(self.n_layer)]
+        self.prev_n = torch.zeros(self.n_layer, dtype=torch.int64, device=dev)   # true node counts of the previous replay
+        self.ws = graph.workspace(self.n)      # keeps the expansion scratch the captured graphs point at alive
+        self.kg_epoch = graph.epoch
         self.L = None
         self.scores = None
         self.version = 0
@@ -99,6 +105,7 @@ class TrainStepRunner(object):
         q_sub, q_rel = self.sub, self.rel
         batch = torch.arange(n, device=dev)
         fr = g.frontier_from_nodes(torch.stack([batch, q_sub], dim=1), n)
+        self.fr0 = fr
         node_b, node_e = batch.to(torch.int32), q_sub.to(torch.int32)
         onehot = torch.zeros((n, 2 * m.n_rel + 1), dtype=torch.float32, device=dev)
         onehot.scatter_(1, q_rel[:, None], 1.0)
@@ -137,6 +144,10 @@ class TrainStepRunner(object):
                                            ptr(layer.W_h.weight), ptr(gate.weight_ih_l0), ptr(gate.weight_hh_l0),
                                            ptr(gate.bias_ih_l0), ptr(gate.bias_hh_l0), self.act_code, ptr(mask),
                                            ptr(self.hidden[i]), ptr(self.saved[i]), stream_ptr()))
+            planes = (C.c_void_p * 8)(self.agg[i].data_ptr(), self.hidden[i].data_ptr(),
+                                      *[self.saved[i][k].data_ptr() for k in range(6)])
+            check(lib.rg_zero_stale_rows(d, ptr(n_dev), ptr(self.prev_n[i:i + 1]), planes, 8, stream_ptr()))
+            _lib.Stats.launches += 2
             L.append(dict(fr_in=fr, fr_out=fr_next, n_dev=n_dev, nb=nb, ne=ne, src=src, rela=rela, Ws8=Ws8, Wr8=Wr8,
                           Wqr8=Wqr8, w8=w8, ar8=ar8, hq=hq, aq8=aq8, as8=as8, hidden_prev=hidden, mask=mask,
                           bwd_seg=bwd_seg, heavy=heavy, fwd_seg=fwd_seg))
@@ -271,9 +282,13 @@ class TrainStepRunner(object):
     CALIBRATION_STEPS = 8      # new variants are only captured during the first replays of a runner
 
     def node_counts(self):
-        """True node count of every layer of the forward just replayed (synchronises)."""
-        c = torch.stack([fr.counts[_lib.RG_CNT_N_OUT] for fr in self.frontiers]).cpu()
-        return [int(x) for x in c]
+        """True node count of every layer of the forward just replayed (synchronises); also surfaces the
+        device-side range check of the query subjects (tensor inputs are not checked on the host)."""
+        c = torch.stack([fr.counts[_lib.RG_CNT_N_OUT] for fr in self.frontiers]
+                        + [self.fr0.counts[_lib.RG_CNT_ERR]]).cpu()
+        if int(c[-1]):
+            raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % self.graph.n_ent)
+        return [int(x) for x in c[:-1]]
 
     def caps_for(self, counts):
         return tuple(next((c for c in self.ladder if c >= k), self.cap) for k in counts)
@@ -314,7 +329,12 @@ class TrainStepRunner(object):
 
 class TrainStepFunction(torch.autograd.Function):
     """scores = forward graph; parameter gradients = backward graph.  The parameters are inputs only
-    so that autograd routes the gradients to them; the kernels read them in place."""
+    so that autograd routes the gradients to them; the kernels read them in place.
+
+    `model.grads_in_place` (off by default): every parameter's `.grad` IS a view of the runner's flat
+    gradient buffer, which the backward graph fills directly -- no per-parameter copies, and a
+    multi-GPU step all-reduces that one buffer with zero packing kernels (dist.allreduce_flat).
+    Valid when this forward is the parameters' only path to the loss (base_model.py:56-61 is)."""
 
     @staticmethod
     def forward(ctx, runner, q_sub, q_rel, *params):
@@ -324,6 +344,10 @@ class TrainStepFunction(torch.autograd.Function):
         _lib.Stats.launches += runner.fwd_launches
         runner.version += 1
         ctx.runner, ctx.version = runner, runner.version
+        ctx.in_place = bool(getattr(runner.model, "grads_in_place", False))
+        if ctx.in_place:
+            for k in runner.names:
+                runner.params[k].grad = runner.grad_views[k]
         return runner.scores.clone()
 
     @staticmethod
@@ -335,6 +359,8 @@ class TrainStepFunction(torch.autograd.Function):
                                "interleaved forward passes")
         r.g_out.copy_(g_scores)
         r.replay_backward()
+        if ctx.in_place:                       # .grad views already hold the result
+            return (None, None, None) + (None,) * len(r.names)
         flat = r.flat_grad.clone()
         out, off = [], 0
         for k in r.names:

@@ -26,4 +26,6 @@ def test_cuda_arm_line_on_tiny_workload(extra):
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0
+    tr = d["subsystems"]["train"]
+    assert tr is not None and tr["ms_per_step"] > 0 and tr["edge_bwd"]["frac"] > 0 and tr["gpu_launches"] > 0

@@ -112,3 +112,17 @@ def test_inductive_forward(fb237):
     ref = model(subs, rels, "inductive").detach()
     mine = O.model_forward(sd, D.ind_graph, subs, rels, 3, "relu", n_ent_out=D.n_ent_ind)
     assert ref.shape == mine.shape and (ref - mine).abs().max().item() < 2e-6
+
+
+def test_staged_reference_copy_is_byte_identical():
+    """oracle/_ref (what the GPU box runs as `kind: "reference"`) == the mounted reference files."""
+    import filecmp
+    import os
+    from oracle import build_ref
+    if not R.is_live():
+        pytest.skip("reference tree not mounted (running from the staged copy)")
+    assert build_ref.stage() > 0
+    for setting in ("transductive", "inductive"):
+        for f in build_ref.FILES:
+            assert filecmp.cmp(os.path.join(build_ref.SRC, "Static", setting, f),
+                               os.path.join(build_ref.DEST, "Static", setting, f), shallow=False), f
