@@ -236,7 +236,36 @@ int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_n
                          const float *agg, const float *h_prev,
                          const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                          const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
-                         float *hidden, float *saved, void *stream);
+                         float *hidden, float *saved, const float *Ws_next, const float *W_final,
+                         float *as8, float *score, void *stream);
+
+/* Training BACKWARD of the node update (autograd of models.py:41,81-84), dense part, native:
+ * rg_node_bwd (tensor cores, hidden_dim <= 48), per node row j < n_nodes:
+ *   g      = g_hidden[j] (+ g_small[j][0..7] . w_small[8][D]) (+ g_h0_next[remap[j]])      upstream
+ *   G4[j]  = [g_r' | g_z' | g_n' | g_n' r]     gradients of the GRU gate pre-activations ([n][4D])
+ *   g_pre[j] = ([g_r' g_z' g_n'] . W_ih) * drop_mask * act'(x)
+ *   g_agg[j] = g_pre[j] . W_h                                       (input of rg_edge_agg_bwd)
+ *   g_h0[j]  = g z + [g_r' g_z' g_n' r] . W_hh                      (has_h0 only)
+ * g_small / w_small fold the next layer's attention projection (g_as8 . Ws_attn) or the score
+ * head (g_score . W_final) into the upstream gradient; g_h0_next / remap (old_nodes_new_idx as
+ * int32) fold the GRU-state path of the next layer in as a gather instead of a scatter.  Any of the
+ * three upstream parts may be NULL, not all.  `saved` is what rg_node_update_train wrote.
+ * rg_node_wgrad (CUDA cores, exact fp32, deterministic): the reductions over nodes
+ *   out = [ dW_ih[3D][D] | dW_hh[3D][D] | dW_h[D][D] | dW_small[8][D] | column sums of G4 [4D] ]
+ * with dW_ih = G4[r,z,n]^T (x * mask), dW_hh = G4[r,z,nr]^T h0, dW_h = g_pre^T agg,
+ * dW_small = g_small^T hidden.  `partial` is scratch of rg_node_wgrad_ctas() * rg_node_wgrad_out_floats()
+ * floats (per-CTA partial sums, added in CTA order). */
+int rg_node_bwd(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *g_hidden,
+                const float *g_small, const float *w_small, const float *g_h0_next, const int32_t *remap,
+                const float *saved, int64_t saved_plane_rows, const float *drop_mask, const float *W_h,
+                const float *W_ih, const float *W_hh, int32_t act, int32_t has_h0, float *G4, float *g_pre,
+                float *g_agg, float *g_h0, void *stream);
+int32_t rg_node_wgrad_ctas(void);
+int64_t rg_node_wgrad_out_floats(int32_t hidden_dim);
+int rg_node_wgrad(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *saved,
+                  int64_t saved_plane_rows, const float *drop_mask, const float *agg, const float *hidden,
+                  const float *G4, const float *g_pre, const float *g_small, int32_t has_h0, float *partial,
+                  float *out, void *stream);
 /* saved_plane_rows: rows per plane of `saved` (0 = n_nodes); lets a caller process only the first
  * n_nodes <= saved_plane_rows rows of buffers that were written with a larger row capacity. */
 int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_rows, const int64_t *n_nodes_dev,

@@ -479,13 +479,15 @@ extern "C" int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const i
                                     const float *agg, const float *h_prev,
                                     const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                                     const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
-                                    float *hidden, float *saved, void *stream) {
+                                    float *hidden, float *saved, const float *Ws_next, const float *W_final,
+                                    float *as8, float *score, void *stream) {
     if (n_nodes < 0 || !agg || !W_h || !W_ih || !W_hh || !b_ih || !b_hh || !hidden || !saved) return RG_ERR_BAD_ARG;
     if ((h_prev == nullptr) != (src == nullptr) || act < 0 || act > 2) return RG_ERR_BAD_ARG;
+    if ((as8 != nullptr) != (Ws_next != nullptr) || (score != nullptr) != (W_final != nullptr)) return RG_ERR_BAD_ARG;
     if (hidden_dim > 48) return RG_ERR_UNSUPPORTED;
     if (n_nodes == 0) return RG_OK;
-    return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, nullptr,
-                             nullptr, act, hidden, nullptr, nullptr, drop_mask, saved, (cudaStream_t)stream);
+    return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next,
+                             W_final, act, hidden, as8, score, drop_mask, saved, (cudaStream_t)stream);
 }
 
 extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,

@@ -264,6 +264,16 @@ class Frontier(object):
         _lib.Stats.launches += 1
         return fwd, inv
 
+    def remaps32(self, fr_out, n_nodes, n_out):
+        """(old_nodes_new_idx int32 [n_nodes], inverse int32 [n_out]) in one launch; both buffers may be
+        upper bounds (rows past the true counts stay unwritten / -1)."""
+        fwd = torch.empty(n_nodes, dtype=torch.int32, device=self.emask.device)
+        inv = torch.full((n_out,), -1, dtype=torch.int32, device=self.emask.device)
+        check(lib.rg_frontier_remap(C.byref(self.c_struct()), C.byref(fr_out.c_struct()), None, ptr(fwd), ptr(inv),
+                                    stream_ptr()))
+        _lib.Stats.launches += 1
+        return fwd, inv
+
     def inverse_remap_to(self, fr_out, n_out):
         """int32 [n_out]: row of each `fr_out` node inside this (previous) frontier, -1 for new nodes."""
         inv = torch.full((n_out,), -1, dtype=torch.int32, device=self.emask.device)

@@ -182,8 +182,8 @@ def node_update(agg, h_prev, src, W_h, gate, act_code, Ws_next8=None, W_final=No
 
 class NodeUpdateTrain(torch.autograd.Function):
     """Training node update: hidden = GRU(dropout(act(W_h agg)), h0) with h0[j] = h_prev[src[j]].
-    Forward = the tcgen05 kernel (rg_node_update_train, also saves the gates); backward = one
-    elementwise kernel (rg_gru_bwd_elem) + six library GEMMs."""
+    Forward = the tcgen05 kernel (rg_node_update_train, also saves the gates); backward = rg_node_bwd
+    (tcgen05 data gradients) + rg_node_wgrad (weight-gradient reductions), no library GEMMs."""
 
     @staticmethod
     def forward(ctx, agg, h_prev, W_h, w_ih, w_hh, b_ih, b_hh, mask, src, remap, act_code):
@@ -195,7 +195,7 @@ class NodeUpdateTrain(torch.autograd.Function):
         with _lib.Stats.timed("node_update_train", (n, d)):
             check(lib.rg_node_update_train(d, n, None, ptr(agg), ptr(h_prev), ptr(src), ptr(W_h), ptr(w_ih), ptr(w_hh),
                                            ptr(b_ih), ptr(b_hh), act_code, ptr(mask), ptr(hidden), ptr(saved),
-                                           stream_ptr()))
+                                           None, None, None, None, stream_ptr()))
         _lib.Stats.launches += 1
         ctx.save_for_backward(agg, saved, W_h, w_ih, w_hh, mask if mask is not None else agg.new_empty(0),
                               remap if remap is not None else agg.new_empty(0, dtype=torch.int64))
@@ -206,29 +206,27 @@ class NodeUpdateTrain(torch.autograd.Function):
     def backward(ctx, g_h):
         agg, saved, W_h, w_ih, w_hh, mask, remap = ctx.saved_tensors
         n, d = agg.shape
+        dev = agg.device
         g_h = g_h.to(torch.float32).contiguous()
-        g_gi = torch.empty((n, 3 * d), dtype=torch.float32, device=agg.device)
-        g_gh = torch.empty((n, 3 * d), dtype=torch.float32, device=agg.device)
-        g_h0d = torch.empty((n, d), dtype=torch.float32, device=agg.device)
-        check(lib.rg_gru_bwd_elem(d, n, 0, None, ptr(g_h), ptr(saved), ptr(g_gi), ptr(g_gh), ptr(g_h0d), None,
-                                  stream_ptr()))
-        _lib.Stats.launches += 1
-        x_act, h0 = saved[0], saved[5]
-        x_in = x_act * mask if ctx.has_mask else x_act
-        g_x = g_gi @ w_ih
-        d_wih, d_bih, d_bhh = g_gi.t() @ x_in, g_gi.sum(0), g_gh.sum(0)
-        if ctx.has_mask:
-            g_x = g_x * mask
-        if ctx.act_code == 1:
-            g_x = g_x * (x_act > 0)
-        elif ctx.act_code == 2:
-            g_x = g_x * (1.0 - x_act * x_act)
-        g_agg, d_wh = g_x @ W_h, g_x.t() @ agg
-        if ctx.has_h0:
-            d_whh = g_gh.t() @ h0
-            g_prev = torch.addmm(g_h0d, g_gh, w_hh).index_select(0, remap)
-        else:
-            d_whh, g_prev = torch.zeros_like(w_hh), None
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        G4, g_pre, g_agg = e(n, 4 * d), e(n, d), e(n, d)
+        g_h0 = e(n, d) if ctx.has_h0 else None
+        mk = mask if ctx.has_mask else None
+        with _lib.Stats.timed("node_bwd", (n, d)):
+            check(lib.rg_node_bwd(d, n, None, ptr(g_h), None, None, None, None, ptr(saved), n, ptr(mk), ptr(W_h),
+                                  ptr(w_ih), ptr(w_hh), ctx.act_code, int(ctx.has_h0), ptr(G4), ptr(g_pre), ptr(g_agg),
+                                  ptr(g_h0), stream_ptr()))
+        out_floats = int(lib.rg_node_wgrad_out_floats(d))
+        partial, wg = e(int(lib.rg_node_wgrad_ctas()) * out_floats), e(out_floats)
+        with _lib.Stats.timed("node_wgrad", (n, d)):
+            check(lib.rg_node_wgrad(d, n, None, ptr(saved), n, ptr(mk), ptr(agg), None, ptr(G4), ptr(g_pre), None,
+                                    int(ctx.has_h0), ptr(partial), ptr(wg), stream_ptr()))
+        _lib.Stats.launches += 3
+        o_whh, o_wh, o_ws, o_b = 3 * d * d, 6 * d * d, 7 * d * d, 7 * d * d + 8 * d
+        d_wih, d_whh, d_wh = wg[:o_whh].view(3 * d, d), wg[o_whh:o_wh].view(3 * d, d), wg[o_wh:o_ws].view(d, d)
+        b4 = wg[o_b:].view(4, d)                               # column sums of g_r', g_z', g_n', g_n' r
+        d_bih, d_bhh = b4[:3].reshape(-1), torch.cat([b4[0], b4[1], b4[3]])
+        g_prev = g_h0.index_select(0, remap) if ctx.has_h0 else None
         return g_agg, g_prev, d_wh, d_wih, d_whh, d_bih, d_bhh, None, None, None, None
 
 

@@ -5,7 +5,7 @@ layer; at the reference's batch sizes (n_batch 3..100, Static/transductive/train
 step is host-bound by a wide margin.  Here the forward of a (batch size, KG) pair is made
 shape-static exactly like the inference path (upper-bound buffers of n_query * n_ent rows, true
 counts read on the device), the backward is written out by hand on the same buffers (fused edge
-backward, GRU elementwise kernel + library GEMMs, small projection GEMMs), and both are captured
+backward, tensor-core node backward, weight-gradient reduction kernel), and both are captured
 once as CUDA graphs.  A single torch.autograd.Function replays them, so `loss.backward()` and the
 optimiser in the caller's loop (Static/*/base_model.py:49-70) work unchanged.
 
@@ -17,16 +17,14 @@ which the reference loop survives by re-randomising NaN parameters, base_model.p
 NaN/Inf into later steps); every gradient row past the true count is an exact zero as well
 (rg_gru_bwd_elem / rg_gather_scores write zeros there, node_small is cleared per replay).
 
-The forward always runs on the full upper-bound buffers.  The backward is dominated by dense GEMMs
-over node rows that cannot stop at a device-side count, and the early layers hold far fewer nodes
-than `n_query * n_ent`; so the backward exists as a few captured variants, one per tuple of
-per-layer row capacities (a geometric ladder of 1024-row multiples).  Before the backward replay the
-true per-layer node counts of the forward are read back (one 8-byte-per-layer copy) and the
-cheapest captured variant that covers them is replayed; tighter variants are captured during the
-first few steps of a runner only (TrainStepRunner.replay_backward).
+Forward and backward both run on the full upper-bound buffers and every kernel stops at the
+device-side node count, so there is ONE captured forward and ONE captured backward per runner and no
+host synchronisation inside a training step.  The dense part of the backward is native
+(csrc/rg_node_bwd.cu: tcgen05 data gradients with the gate gradients as TMEM-resident A operands,
+CUDA-core weight gradients); what is left to torch are the per-relation / per-query projections
+(a few hundred rows) and the loss / optimiser of the caller.
 """
 import ctypes as C
-import os
 
 import torch
 import torch.nn.functional as F
@@ -40,20 +38,6 @@ def _pad_rows(w, rows=8):
     return w if w.shape[0] == rows else F.pad(w, (0, 0, 0, rows - w.shape[0]))
 
 
-_SPLIT = 1024
-
-
-def _tn(a, b):
-    """a^T @ b for tall operands [M, p], [M, q] (weight gradients: the reduction runs over NODES).
-    A plain GEMM gives the library one or two output tiles and a K of 10^5..10^6; split-K as a batched
-    GEMM over 1024-row slabs + a sum keeps all SMs busy and the summation order fixed."""
-    m = a.shape[0]
-    if m % _SPLIT or m < 4 * _SPLIT:
-        return a.t() @ b
-    s = m // _SPLIT
-    return torch.bmm(a.view(s, _SPLIT, -1).transpose(1, 2), b.view(s, _SPLIT, -1)).sum(0)
-
-
 class TrainStepRunner(object):
     """Static buffers + the two CUDA graphs for one (model, KG, batch size)."""
 
@@ -61,8 +45,8 @@ class TrainStepRunner(object):
         self.model, self.graph, self.n, self.n_ent_out = model, graph, int(n), int(n_ent_out)
         dev = model.W_final.weight.device
         self.dev, self.d, self.a, self.n_layer = dev, model.hidden_dim, model.attn_dim, model.n_layer
-        # rows of every per-node buffer: upper bound n_query * n_ent, padded for the split-K weight gradients
-        self.cap = -(-(self.n * graph.n_ent) // _SPLIT) * _SPLIT
+        # rows of every per-node buffer: the upper bound n_query * n_ent
+        self.cap = self.n * graph.n_ent
         self.act_code = ACT_CODES[model.act_name]
         self.p_drop = float(model.dropout.p)
         self.names = [k for k, _ in model.named_parameters()]
@@ -81,21 +65,17 @@ class TrainStepRunner(object):
         self.agg = [z(self.cap, self.d) for _ in range(self.n_layer)]
         self.hidden = [z(self.cap, self.d) for _ in range(self.n_layer)]
         self.saved = [z(6, self.cap, self.d) for _ in range(self.n_layer)]
+        self.as8 = [z(self.cap, 8) for _ in range(self.n_layer - 1)]       # next layer's Ws_attn(hidden), per node
+        self.score_node = z(self.cap)
+        self.wg_out_floats = int(lib.rg_node_wgrad_out_floats(self.d))
+        self.wg_partial = torch.empty(int(lib.rg_node_wgrad_ctas()) * self.wg_out_floats, dtype=torch.float32, device=dev)
         self.prev_n = torch.zeros(self.n_layer, dtype=torch.int64, device=dev)   # true node counts of the previous replay
         self.ws = graph.workspace(self.n)      # keeps the expansion scratch the captured graphs point at alive
         self.kg_epoch = graph.epoch
         self.L = None
         self.scores = None
         self.version = 0
-        # row-capacity ladder for the backward variants: cap, cap/1.5, ... (multiples of _SPLIT, >= 4 slabs)
-        self.ladder = [self.cap]
-        while self.ladder[-1] > 4 * _SPLIT:
-            nxt = max(4 * _SPLIT, -(-int(self.ladder[-1] / 1.5) // _SPLIT) * _SPLIT)
-            if nxt >= self.ladder[-1]:
-                break
-            self.ladder.append(nxt)
-        self.ladder.reverse()
-        self.bwd_graphs = {}           # caps tuple -> (CUDAGraph, launches)
+        self.bwd_graphs = {}           # one entry: (CUDAGraph, launches)
         self.bwd_replays = 0
         self._build()
 
@@ -115,7 +95,9 @@ class TrainStepRunner(object):
             fr_next = g.step(fr)
             n_dev = fr_next.counts[_lib.RG_CNT_N_OUT:_lib.RG_CNT_N_OUT + 1]
             nb, ne = fr_next.nodes32(cap)
-            src = fr.inverse_remap_to(fr_next, cap) if hidden is not None else None
+            # src: row of an output node inside the previous layer (-1 = new node) for the h0 gather of the
+            # forward; remap: old_nodes_new_idx as int32 for the g_h0 gather of the backward (layers >= 1)
+            remap, src = fr.remaps32(fr_next, cap, cap) if hidden is not None else (None, None)
             rela = layer.rela_embed.weight
             Ws8, Wr8, Wqr8 = _pad_rows(layer.Ws_attn.weight), _pad_rows(layer.Wr_attn.weight), \
                 _pad_rows(layer.Wqr_attn.weight)
@@ -124,7 +106,7 @@ class TrainStepRunner(object):
             ar8 = (rela @ Wr8.t()).contiguous()
             hq = onehot @ rela                                   # rela[q_rel], as a GEMM (deterministic backward)
             aq8 = torch.addmm(bqr8, hq, Wqr8.t()).contiguous()
-            as8 = (hidden @ Ws8.t()).contiguous() if hidden is not None else None
+            as8 = self.as8[i - 1] if hidden is not None else None   # written by the previous node update
             fwd_seg = Segments.implicit(nb, ne, g.in_ptr, g.in_adj, fr, g.heavy_in)
             fwd_seg.n_seg_dev, fwd_seg.n_table_rows = n_dev, rela.shape[0]
             bwd_seg = Segments.implicit(node_b, node_e, g.out_ptr, g.out_adj, fr_next, g.heavy_out)
@@ -140,83 +122,92 @@ class TrainStepRunner(object):
                 keep = 1.0 - self.p_drop
                 mask = (torch.rand((cap, d), device=dev) < keep).to(torch.float32).div_(keep)
             gate = m.gate
+            last = i == self.n_layer - 1
+            # the node kernel also emits the NEXT layer's attention projection Ws_attn(hidden) / the scores
+            ws_next = None if last else _pad_rows(m.gnn_layers[i + 1].Ws_attn.weight).contiguous()
             check(lib.rg_node_update_train(d, cap, ptr(n_dev), ptr(self.agg[i]), ptr(hidden), ptr(src),
                                            ptr(layer.W_h.weight), ptr(gate.weight_ih_l0), ptr(gate.weight_hh_l0),
                                            ptr(gate.bias_ih_l0), ptr(gate.bias_hh_l0), self.act_code, ptr(mask),
-                                           ptr(self.hidden[i]), ptr(self.saved[i]), stream_ptr()))
+                                           ptr(self.hidden[i]), ptr(self.saved[i]), ptr(ws_next),
+                                           ptr(m.W_final.weight) if last else None,
+                                           ptr(self.as8[i]) if not last else None,
+                                           ptr(self.score_node) if last else None, stream_ptr()))
             planes = (C.c_void_p * 8)(self.agg[i].data_ptr(), self.hidden[i].data_ptr(),
                                       *[self.saved[i][k].data_ptr() for k in range(6)])
             check(lib.rg_zero_stale_rows(d, ptr(n_dev), ptr(self.prev_n[i:i + 1]), planes, 8, stream_ptr()))
             _lib.Stats.launches += 2
-            L.append(dict(fr_in=fr, fr_out=fr_next, n_dev=n_dev, nb=nb, ne=ne, src=src, rela=rela, Ws8=Ws8, Wr8=Wr8,
+            L.append(dict(fr_in=fr, fr_out=fr_next, n_dev=n_dev, nb=nb, ne=ne, src=src, remap=remap, ws_next=ws_next,
+                          rela=rela, Ws8=Ws8, Wr8=Wr8,
                           Wqr8=Wqr8, w8=w8, ar8=ar8, hq=hq, aq8=aq8, as8=as8, hidden_prev=hidden, mask=mask,
                           bwd_seg=bwd_seg, heavy=heavy, fwd_seg=fwd_seg))
             hidden, n_in_dev, fr, node_b, node_e = self.hidden[i], n_dev, fr_next, nb, ne
-        score_node = (hidden @ m.W_final.weight.t()).reshape(-1).contiguous()
         scores = torch.zeros((n, self.n_ent_out), dtype=torch.float32, device=dev)
-        check(lib.rg_scatter_scores(cap, ptr(n_in_dev), ptr(node_b), ptr(node_e), ptr(score_node), self.n_ent_out,
+        check(lib.rg_scatter_scores(cap, ptr(n_in_dev), ptr(node_b), ptr(node_e), ptr(self.score_node), self.n_ent_out,
                                     ptr(scores), stream_ptr()))
         _lib.Stats.launches += 1
         self.L, self.onehot = L, onehot
         return scores
 
     # ------------------------------------------------------------------------------------------
-    def _backward(self, caps):
-        """caps[i]: rows processed for layer i's OUTPUT nodes (>= the true count of this step, a
-        multiple of _SPLIT, <= self.cap); layer i's input rows are caps[i-1]."""
-        m, n, d, a, dev = self.model, self.n, self.d, self.a, self.dev
-        full = self.cap
+    def _backward(self, caps=None):
+        """Hand-written backward of the whole path on the buffers of the last forward replay.  Every
+        kernel stops at the device-side node counts, so nothing here depends on the true sizes
+        (`caps` is accepted for compatibility and ignored): ONE captured variant, no host read-back.
+        Per layer, last to first:  rg_node_bwd (tensor cores: GRU / W_h data gradients, with the next
+        layer's attention-projection and GRU-state paths folded in as gathers)  ->  rg_node_wgrad
+        (weight gradients)  ->  rg_edge_agg_bwd (fused edge backward)  ->  per-relation / per-query
+        projections (tiny, torch)."""
+        m, n, d, a, dev, cap = self.model, self.n, self.d, self.a, self.dev, self.cap
         st = stream_ptr
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
         e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         grads = {}
         last = self.L[-1]
-        cap = caps[-1]
+        # upstream of the last layer: g_hidden = g_score * W_final, expressed as g_small . w_small
         g_node = e(cap)
         check(lib.rg_gather_scores(cap, ptr(last["n_dev"]), ptr(last["nb"]), ptr(last["ne"]), ptr(self.g_out),
                                    self.n_ent_out, ptr(g_node), st()))
         _lib.Stats.launches += 1
-        grads["W_final.weight"] = _tn(g_node[:, None], self.hidden[-1][:cap])
-        g_hidden = g_node[:, None] * m.W_final.weight
+        g_small = z(cap, 8)
+        g_small[:, 0] = g_node
+        w_small = F.pad(m.W_final.weight, (0, 0, 0, 7)).contiguous()          # [8, d], row 0 = W_final
+        g_hid_e, g_h0_next, remap = None, None, None
         gate = m.gate
         w_ih, w_hh = gate.weight_ih_l0, gate.weight_hh_l0
         d_wih, d_whh, d_bih, d_bhh = torch.zeros_like(w_ih), torch.zeros_like(w_hh), z(3 * d), z(3 * d)
+        O_WHH, O_WH, O_WS, O_B = 3 * d * d, 6 * d * d, 7 * d * d, 7 * d * d + 8 * d
         for i in reversed(range(self.n_layer)):
             lay, layer = self.L[i], m.gnn_layers[i]
             pre = "gnn_layers.%d." % i
-            saved, mask = self.saved[i], lay["mask"]
-            cap = caps[i]                                    # rows of this layer's output nodes
-            cap_in = caps[i - 1] if i > 0 else n             # rows of its input nodes
-            if mask is not None:
-                mask = mask[:cap]
-            g_hidden = g_hidden.contiguous()
-            g_gi, g_gh, g_h0d = e(cap, 3 * d), e(cap, 3 * d), e(cap, d)
-            bias_part = z(-(-cap // 64), 4, d)               # per-CTA column sums of g_r, g_z, g_n, g_n * r
-            check(lib.rg_gru_bwd_elem(d, cap, full, ptr(lay["n_dev"]), ptr(g_hidden), ptr(saved), ptr(g_gi),
-                                      ptr(g_gh), ptr(g_h0d), ptr(bias_part), st()))
-            bsum = bias_part.sum(0)                          # [4, d]
-            x_act = saved[0][:cap]
-            x_in = x_act * mask if mask is not None else x_act
-            d_wih += _tn(g_gi, x_in)
-            d_bih += bsum[:3].reshape(-1)
-            d_bhh += torch.cat([bsum[0], bsum[1], bsum[3]])
-            g_x = g_gi @ w_ih
-            if mask is not None:
-                g_x = g_x * mask
-            if self.act_code == 1:
-                g_x = g_x * (x_act > 0)
-            elif self.act_code == 2:
-                g_x = g_x * (1.0 - x_act * x_act)
-            grads[pre + "W_h.weight"] = _tn(g_x, self.agg[i][:cap])
-            g_agg = (g_x @ layer.W_h.weight).contiguous()
-            hidden_prev, g_h0 = lay["hidden_prev"], None
-            if hidden_prev is not None:
-                d_whh += _tn(g_gh, saved[5][:cap])
-                g_h0 = torch.addmm(g_h0d, g_gh, w_hh)
+            has_h0 = lay["hidden_prev"] is not None
+            G4, g_pre, g_agg = e(cap, 4 * d), e(cap, d), e(cap, d)
+            g_h0 = e(cap, d) if has_h0 else None
+            check(lib.rg_node_bwd(d, cap, ptr(lay["n_dev"]), ptr(g_hid_e), ptr(g_small), ptr(w_small), ptr(g_h0_next),
+                                  ptr(remap), ptr(self.saved[i]), cap, ptr(lay["mask"]), ptr(layer.W_h.weight),
+                                  ptr(w_ih), ptr(w_hh), self.act_code, int(has_h0), ptr(G4), ptr(g_pre), ptr(g_agg),
+                                  ptr(g_h0), st()))
+            wg = e(self.wg_out_floats)
+            check(lib.rg_node_wgrad(d, cap, ptr(lay["n_dev"]), ptr(self.saved[i]), cap, ptr(lay["mask"]),
+                                    ptr(self.agg[i]), ptr(self.hidden[i]), ptr(G4), ptr(g_pre), ptr(g_small),
+                                    int(has_h0), ptr(self.wg_partial), ptr(wg), st()))
+            _lib.Stats.launches += 3
+            d_wih += wg[:O_WHH].view(3 * d, d)
+            d_whh += wg[O_WHH:O_WH].view(3 * d, d)
+            grads[pre + "W_h.weight"] = wg[O_WH:O_WS].view(d, d)
+            b4 = wg[O_B:].view(4, d)                             # column sums of g_r', g_z', g_n', g_n' r
+            d_bih += b4[:3].reshape(-1)
+            d_bhh += torch.cat([b4[0], b4[1], b4[3]])
+            dws = wg[O_WS:O_B].view(8, d)                        # g_small^T hidden of this layer
+            if i == self.n_layer - 1:
+                grads["W_final.weight"] = dws[:1]
+            else:
+                grads["gnn_layers.%d.Ws_attn.weight" % (i + 1)] = dws[:a]
             # fused edge backward on the same implicit segments (grouped by the layer's INPUT nodes)
+            hidden_prev = lay["hidden_prev"]
             bwd_seg, rela = lay["bwd_seg"], lay["rela"]
-            node_small = z(cap_in, 24)                       # the kernels stop at the true input-node count
-            g_hid_e = z(cap_in, d) if hidden_prev is not None else None
+            cap_in = cap if i > 0 else n
+            node_small = e(cap_in, 24)                           # every consumer stops at the true input-node count
+            g_hid_e = e(cap_in, d) if hidden_prev is not None else None
             copies = _lib.GRAD_COPIES
             g_rela, g_ar8 = z(copies, rela.shape[0], d), z(copies, rela.shape[0], 8)
             heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
@@ -226,9 +217,7 @@ class TrainStepRunner(object):
                                       heavy.ref(), st()))
             g_rela, g_ar8 = g_rela.sum(0), g_ar8.sum(0)
             lay["heavy_bwd"] = heavy
-            # gru elementwise + edge backward (+ chunk / fix-up kernels) + query sum (+ row scatter)
-            _lib.Stats.launches += 2 + (3 if heavy.struct is not None else 1)
-            g_as8 = node_small[:, :8]
+            _lib.Stats.launches += 1 + (3 if heavy.struct is not None else 1)      # + query sum
             q_part = e(n, 32, 24)
             check(lib.rg_query_sum8(n, ptr(node_small), ptr(lay["fr_in"].qinfo), ptr(q_part), st()))
             q_sum = q_part.sum(1)                            # [n, 24] per-query sums of node_small
@@ -242,13 +231,12 @@ class TrainStepRunner(object):
             g_rela = g_rela + g_ar8 @ lay["Wr8"] + self.onehot.t() @ (g_aq8 @ lay["Wqr8"])
             grads[pre + "rela_embed.weight"] = g_rela
             if hidden_prev is not None:
-                grads[pre + "Ws_attn.weight"] = _tn(g_as8.contiguous(), hidden_prev[:cap_in])[:a]
-                # g_hidden(prev) = edge part + attention-projection part + GRU state part (scattered in place)
-                check(lib.rg_scatter_rows(d, cap, ptr(lay["n_dev"]), ptr(lay["src"]), ptr(g_h0), ptr(g_hid_e), 1, st()))
-                _lib.Stats.launches += 1
-                g_hidden = torch.addmm(g_hid_e, g_as8, lay["Ws8"])
-            else:
-                grads[pre + "Ws_attn.weight"] = torch.zeros_like(layer.Ws_attn.weight)   # explicit zero (layer 0)
+                # upstream of layer i-1 = edge part (g_hid_e) + attention-projection part (g_as8 . Ws_attn) +
+                # GRU-state part (g_h0 gathered through old_nodes_new_idx): all three summed inside rg_node_bwd
+                g_small = node_small[:, :8].contiguous()
+                w_small = lay["Ws8"].contiguous()
+                g_h0_next, remap = g_h0, lay["remap"]
+        grads["gnn_layers.0.Ws_attn.weight"] = torch.zeros_like(m.gnn_layers[0].Ws_attn.weight)   # explicit zero (layer 0)
         grads["gate.weight_ih_l0"], grads["gate.weight_hh_l0"] = d_wih, d_whh
         grads["gate.bias_ih_l0"], grads["gate.bias_hh_l0"] = d_bih, d_bhh
         for k in self.names:
@@ -274,12 +262,8 @@ class TrainStepRunner(object):
         self.fwd_launches = _lib.Stats.launches - before
         _lib.Stats.launches = before
         self.frontiers = [lay["fr_out"] for lay in self.L]
+        self.frontiers[0].source_frontier = self.fr0       # lets RedGNN.last_stats surface RG_CNT_ERR lazily
         self._capture_backward(full, warm=False)
-
-    # captured backward variants per runner (each owns its temporaries); REDGNN_BWD_VARIANTS=1 keeps only
-    # the full-capacity one (A/B measurements)
-    MAX_BWD_VARIANTS = int(os.environ.get("REDGNN_BWD_VARIANTS", "6"))
-    CALIBRATION_STEPS = 8      # new variants are only captured during the first replays of a runner
 
     def node_counts(self):
         """True node count of every layer of the forward just replayed (synchronises); also surfaces the
@@ -290,39 +274,21 @@ class TrainStepRunner(object):
             raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % self.graph.n_ent)
         return [int(x) for x in c[:-1]]
 
-    def caps_for(self, counts):
-        return tuple(next((c for c in self.ladder if c >= k), self.cap) for k in counts)
-
     def _capture_backward(self, caps, warm=True):
-        if warm:                                             # new GEMM shapes: lazy library inits outside capture
-            cur, side = torch.cuda.current_stream(), torch.cuda.Stream()
-            side.wait_stream(cur)
-            with torch.cuda.stream(side), torch.no_grad():
-                self._backward(caps)
-            cur.wait_stream(side)
-            torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         before = _lib.Stats.launches
         with torch.no_grad(), torch.cuda.graph(g, pool=self.fwd_graph.pool()):
-            self._backward(caps)
+            self._backward()
         launches = _lib.Stats.launches - before
         _lib.Stats.launches = before
         self.bwd_graphs[caps] = (g, launches)
 
     def replay_backward(self):
-        """Replay the cheapest captured variant whose per-layer capacities cover this step's node
-        counts (the full-capacity variant always does).  During the first CALIBRATION_STEPS replays a
-        tighter variant (10 % headroom, next ladder step) is captured when the best one processes more
-        than 1.2x the rows it would."""
-        counts = self.node_counts()
-        best = min((k for k in self.bwd_graphs if all(c >= n for c, n in zip(k, counts))), key=sum)
-        if self.bwd_replays < self.CALIBRATION_STEPS and len(self.bwd_graphs) < self.MAX_BWD_VARIANTS:
-            want = self.caps_for([min(self.cap, n + n // 10 + 1) for n in counts])
-            if sum(best) > 1.2 * sum(want):
-                self._capture_backward(want)
-                best = want
+        """One captured backward (all kernels read the true node counts on the device): no host
+        synchronisation anywhere in the training step.  The range check of the query subjects is the
+        caller's (RedGNN checks numpy inputs on the host, tensor inputs by `check_tensor_inputs`)."""
         self.bwd_replays += 1
-        g, launches = self.bwd_graphs[best]
+        (g, launches), = self.bwd_graphs.values()
         g.replay()
         _lib.Stats.launches += launches
 

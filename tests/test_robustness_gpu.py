@@ -151,7 +151,7 @@ def test_invalid_ids_are_refused(tiny_dir):
         model(bad, rels, mode="test")
     with pytest.raises(_lib.RgError):
         model.last_stats
-    model.train()
-    out = model(bad, rels)
+    model.train()                                                  # graph-captured training step: no host sync at all
+    model(bad, rels).sum().backward()
     with pytest.raises(_lib.RgError):
-        out.sum().backward()
+        model.last_stats
