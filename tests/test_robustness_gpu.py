@@ -43,7 +43,7 @@ def test_graph_training_recovers_after_a_diverged_step(tiny_dir):
     runner_counts.append(runner.node_counts())
     saved = {k: p.detach().clone() for k, p in model.named_parameters()}
     with torch.no_grad():
-        model.gnn_layers[0].W_h.weight.fill_(float("nan"))   # the diverged step
+        model.gate.weight_ih_l0.fill_(float("nan"))          # the diverged step: NaN gates -> NaN hidden / saved rows
     bad_loss, bad = loss_backward(model, big)
     assert not torch.isfinite(bad_loss)
     with torch.no_grad():                                    # base_model.py:65-69 re-randomises NaN parameters
