@@ -105,12 +105,16 @@ typedef struct rg_segments {
 } rg_segments;
 
 /* Queue for segments longer than RG_HEAVY_CHUNK candidate slots: they are cut into chunks that
- * other warps reduce into `partial`, then summed in chunk order (deterministic). */
-#define RG_HEAVY_CHUNK 512
+ * other warps reduce into `partial`, then summed in chunk order (deterministic).  The persistent
+ * kernels drain the queue themselves (idle warps take chunks while others still work on segments);
+ * the other variants run a second kernel over it. */
+#ifndef RG_HEAVY_CHUNK
+#define RG_HEAVY_CHUNK 256
+#endif
 typedef struct rg_heavy {
     int32_t max_chunks;
     int32_t max_nodes;
-    int32_t *counters;       /* [4] zeroed by the caller: n_chunks, n_nodes, overflow, -       */
+    int32_t *counters;       /* [8] zeroed by the library: n_chunks, n_nodes, overflow, taken, warps done */
     int32_t *chunk_seg;      /* [max_chunks]                                                   */
     int32_t *chunk_idx;      /* [max_chunks]                                                   */
     int32_t *node_seg;       /* [max_nodes]                                                    */

@@ -100,12 +100,16 @@ def plscaled():
 def powerlaw():
     t0 = time.time()
     sp = kg_synth.ArraySplits("powerlaw", seed=0)
-    sd, q, scores, edges = eval_block(sp, 6, 1)
+    sd, q, scores, edges, s64 = eval_block(sp, 6, 1, fp64=True)
     s = scores.numpy().astype(np.float32)[0]
+    s64 = s64.numpy()[0]
     idx = np.sort(np.random.default_rng(5).choice(sp.n_ent, 131072, replace=False))
     fx = {"graph_sha": np.array(tri_sha(sp.test_graph_triples)), "queries": q.astype(np.int64),
           "sample_idx": idx.astype(np.int32), "sample_scores": s[idx], "visited_bits": np.packbits(s != 0),
-          "score_absmax": np.float64(np.abs(s).max()), "edges": np.array(edges, dtype=np.int64), "seed": np.int64(1234)}
+          "sample_scores64": s64[idx].astype(np.float32),
+          "err32": np.float64(np.abs(s.astype(np.float64) - s64).max() / np.abs(s64).max()),
+          "score_absmax": np.float64(np.abs(s64).max()), "edges": np.array(edges, dtype=np.int64), "seed": np.int64(1234)}
+    print("powerlaw fp32 oracle vs fp64: %.3e" % float(fx["err32"]), flush=True)
     np.savez_compressed(os.path.join(OUT, "powerlaw_1q.npz"), **fx)
     print("powerlaw edges", edges, "%.0f s" % (time.time() - t0), flush=True)
 

@@ -108,10 +108,53 @@ __device__ __forceinline__ void enqueue_heavy(const rg_heavy &H, int64_t seg, in
         H.node_base[slot] = base;
         H.node_n[slot] = nch;
     }
-    for (int c = lane; c < nch; c += 32) {
-        H.chunk_seg[base + c] = (int)seg;
-        H.chunk_idx[base + c] = c + 1;
+    // chunk_idx (>= 1) doubles as the "published" flag the in-kernel drain of the persistent kernels polls:
+    // chunk_seg first, then a release store of chunk_idx
+    for (int c = lane; c < nch; c += 32) H.chunk_seg[base + c] = (int)seg;
+    __threadfence();
+    __syncwarp();
+    for (int c = lane; c < nch; c += 32)
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(H.chunk_idx + base + c), "r"(c + 1) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Persistent kernels drain the heavy-chunk queue THEMSELVES: a warp that has run out of segments
+// takes chunks (counters[3]) as soon as their entries are published, until every warp of the grid
+// has finished producing (counters[4] == total_warps) and the queue is empty.  All CTAs of a
+// persistent launch are co-resident (grid <= occupancy x SMs), so the polling cannot deadlock.  The
+// chunk work thereby overlaps the tail of the segment work instead of running as a second,
+// latency-bound kernel behind it.  Returns the chunk to process or -1.  Warp-collective.
+__device__ __forceinline__ int heavy_take(const rg_heavy &H, int total_warps, int lane) {
+    int c = 0;
+    if (lane == 0) {
+        c = atomicAdd(&H.counters[3], 1);
+        unsigned backoff = 256;   // ns; doubles up to ~8 us: thousands of idle warps must not hammer the L2
+                                  // lines of the counters while the working warps stream their atomics
+        for (;;) {
+            if (ld_acquire(&H.counters[2])) { c = -1; break; }   // queue overflow (reported to the caller)
+            int reserved = min(ld_acquire(&H.counters[0]), H.max_chunks);
+            if (c < reserved) {
+                while (ld_acquire(&H.chunk_idx[c]) == 0) {
+                    if (ld_acquire(&H.counters[2])) { c = -1; break; }
+                    __nanosleep(128);
+                }
+                break;
+            }
+            if (ld_acquire(&H.counters[4]) >= total_warps) {     // no producer left: final look at the queue
+                reserved = min(ld_acquire(&H.counters[0]), H.max_chunks);
+                if (c >= reserved) { c = -1; break; }
+                continue;
+            }
+            __nanosleep(backoff);
+            if (backoff < 8192) backoff <<= 1;
+        }
     }
+    return __shfl_sync(RG_FULL_MASK, c, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -435,18 +478,44 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
     const int lane = threadIdx.x & 31;
     const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
     const float ba = __ldg(b_alpha);
-    for (int64_t seg = (int64_t)blockIdx.x * kPWarps + (threadIdx.x >> 5); seg < n_true;
-         seg += (int64_t)gridDim.x * kPWarps) {
-        SegRange r = seg_range<true>(S, seg);
-        int hi = r.hi;
-        if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
-            enqueue_heavy(H, seg, r.hi - r.lo, lane);
-            hi = r.lo + RG_HEAVY_CHUNK;
+    // work loop: this warp's segments (static round robin), then chunks of heavy segments from the queue
+    int64_t seg = (int64_t)blockIdx.x * kPWarps + (threadIdx.x >> 5);
+    const int64_t stride = (int64_t)gridDim.x * kPWarps;
+    bool draining = false;
+    for (;;) {
+        int q, lo, hi;
+        float *dst;
+        if (!draining) {
+            if (seg < n_true) {
+                SegRange r = seg_range<true>(S, seg);
+                q = r.q, lo = r.lo, hi = r.hi;
+                if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
+                    enqueue_heavy(H, seg, r.hi - r.lo, lane);
+                    hi = r.lo + RG_HEAVY_CHUNK;
+                }
+                dst = agg + (size_t)seg * D;
+                seg += stride;
+            } else {
+                if (!has_heavy) break;
+                draining = true;
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(&H.counters[4], 1);
+                }
+                continue;
+            }
+        } else {
+            const int c = heavy_take(H, (int)stride, lane);
+            if (c < 0) break;
+            SegRange r = seg_range<true>(S, (int64_t)H.chunk_seg[c]);
+            q = r.q;
+            lo = r.lo + H.chunk_idx[c] * RG_HEAVY_CHUNK;
+            hi = min(r.hi, lo + RG_HEAVY_CHUNK);
+            dst = H.partial + (size_t)c * D;
         }
         float4 acc[D / 16];
-        fwd_range<D, HAS_HIDDEN, true, true>(S, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, acc, s_rela,
-                                             s_ar8);
-        store_row<D>(agg + (size_t)seg * D, acc, lane);
+        fwd_range<D, HAS_HIDDEN, true, true>(S, q, lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, acc, s_rela, s_ar8);
+        store_row<D>(dst, acc, lane);
     }
 }
 
@@ -834,20 +903,51 @@ __global__ void __launch_bounds__(kPWarpsB * 32, 2) k_edge_bwd_p(rg_segments S, 
     const int lane = threadIdx.x & 31;
     const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
     const float ba = __ldg(b_alpha);
-    for (int64_t seg = (int64_t)blockIdx.x * kPWarpsB + (threadIdx.x >> 5); seg < n_true;
-         seg += (int64_t)gridDim.x * kPWarpsB) {
-        SegRange r = seg_range<true>(S, seg);
-        int hi = r.hi;
-        if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
-            enqueue_heavy(H, seg, r.hi - r.lo, lane);
-            hi = r.lo + RG_HEAVY_CHUNK;
+    // work loop: this warp's segments, then chunks of heavy segments from the queue (see heavy_take)
+    int64_t seg = (int64_t)blockIdx.x * kPWarpsB + (threadIdx.x >> 5);
+    const int64_t stride = (int64_t)gridDim.x * kPWarpsB;
+    bool draining = false;
+    for (;;) {
+        int q, lo, hi;
+        int64_t sg;
+        float *dst_g, *dst_s;
+        if (!draining) {
+            if (seg < n_true) {
+                SegRange r = seg_range<true>(S, seg);
+                q = r.q, lo = r.lo, hi = r.hi, sg = seg;
+                if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
+                    enqueue_heavy(H, seg, r.hi - r.lo, lane);
+                    hi = r.lo + RG_HEAVY_CHUNK;
+                }
+                dst_g = g_hidden ? g_hidden + (size_t)seg * D : nullptr;
+                dst_s = node_small + (size_t)seg * 24;
+                seg += stride;
+            } else {
+                if (!has_heavy) break;
+                draining = true;
+                if (lane == 0) {
+                    __threadfence();
+                    atomicAdd(&H.counters[4], 1);
+                }
+                continue;
+            }
+        } else {
+            const int c = heavy_take(H, (int)stride, lane);
+            if (c < 0) break;
+            sg = H.chunk_seg[c];
+            SegRange r = seg_range<true>(S, sg);
+            q = r.q;
+            lo = r.lo + H.chunk_idx[c] * RG_HEAVY_CHUNK;
+            hi = min(r.hi, lo + RG_HEAVY_CHUNK);
+            dst_g = H.partial + (size_t)c * (D + 24);
+            dst_s = dst_g + D;
         }
         float4 G[D / 16];
         BwdSmall sm;
-        bwd_range<D, HAS_HIDDEN, true, true>(S, seg, r.q, r.lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, g_agg, g_rela,
-                                             g_ar8, G, sm, s_rela, s_ar8);
-        if (g_hidden) store_row<D>(g_hidden + (size_t)seg * D, G, lane);
-        store_small(node_small + (size_t)seg * 24, sm, lane);
+        bwd_range<D, HAS_HIDDEN, true, true>(S, sg, q, lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, g_agg, g_rela, g_ar8,
+                                             G, sm, s_rela, s_ar8);
+        if (dst_g) store_row<D>(dst_g, G, lane);
+        store_small(dst_s, sm, lane);
     }
 }
 
@@ -921,6 +1021,10 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
     const int has_heavy = heavy && heavy->max_chunks > 0 && heavy->max_nodes > 0;
     if (has_heavy) H = *heavy;
     if (seg->n_seg == 0) return RG_OK;
+    if (has_heavy) {   // queue state: counters and the published flags (chunk_idx) start from zero
+        RG_CUDA_CALL(cudaMemsetAsync(H.counters, 0, 8 * sizeof(int32_t), st));
+        RG_CUDA_CALL(cudaMemsetAsync(H.chunk_idx, 0, (size_t)H.max_chunks * sizeof(int32_t), st));
+    }
     const size_t tab_bytes = (size_t)seg->n_table_rows * (D + 8) * sizeof(float);
     bool persistent = false;
     if constexpr (IM) {
@@ -955,8 +1059,10 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
         RG_LAUNCH_CHECK();
     }
     if (has_heavy) {
-        k_edge_fwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, H);
-        RG_LAUNCH_CHECK();
+        if (!persistent) {   // the persistent kernel has drained the queue itself
+            k_edge_fwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, H);
+            RG_LAUNCH_CHECK();
+        }
         k_heavy_fixup<<<kHeavyGrid, kBlock, 0, st>>>(H, D, agg, D, nullptr, 0);
         RG_LAUNCH_CHECK();
     }
@@ -971,6 +1077,10 @@ int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, co
     const int has_heavy = heavy && heavy->max_chunks > 0 && heavy->max_nodes > 0;
     if (has_heavy) H = *heavy;
     if (seg->n_seg == 0) return RG_OK;
+    if (has_heavy) {   // queue state: counters and the published flags (chunk_idx) start from zero
+        RG_CUDA_CALL(cudaMemsetAsync(H.counters, 0, 8 * sizeof(int32_t), st));
+        RG_CUDA_CALL(cudaMemsetAsync(H.chunk_idx, 0, (size_t)H.max_chunks * sizeof(int32_t), st));
+    }
     const size_t tab_bytes = (size_t)seg->n_table_rows * (D + 8) * sizeof(float);
     bool persistent = false;
     if constexpr (IM) {
@@ -1006,9 +1116,11 @@ int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, co
         RG_LAUNCH_CHECK();
     }
     if (has_heavy) {
-        k_edge_bwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha,
-                                                                    g_agg, g_rela, g_ar8, copies, H);
-        RG_LAUNCH_CHECK();
+        if (!persistent) {
+            k_edge_bwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha,
+                                                                        g_agg, g_rela, g_ar8, copies, H);
+            RG_LAUNCH_CHECK();
+        }
         k_heavy_fixup<<<kHeavyGrid, kBlock, 0, st>>>(H, D + 24, g_hidden, D, node_small, 24);
         RG_LAUNCH_CHECK();
     }

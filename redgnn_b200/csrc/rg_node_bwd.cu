@@ -16,8 +16,8 @@
 //   rg_node_wgrad  (k_node_wgrad, CUDA cores, exact fp32, deterministic): the reductions over NODES
 //       dW_ih = G[r,z,n]^T x_in   dW_hh = G[r,z,nr]^T h0   dW_h = g_pre^T agg   dW_small = g_small^T hidden
 //       bias sums = column sums of G4
-//     as 8x8 register tiles over 32-node slabs staged in shared memory; per-CTA partials are summed in
-//     CTA order by k_wgrad_reduce (no atomics).
+//     as 8x8 register tiles over 16-node slabs staged in shared memory by TMA bulk copies (3-deep
+//     mbarrier ring); per-CTA partials are summed in a fixed order by k_wgrad_reduce (no atomics).
 // Both stop at the device-side node count, so upper-bound (shape-static) buffers cost nothing.
 #include "rg_tc.cuh"
 
@@ -53,6 +53,7 @@ __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const float (&v
           "r"(__float_as_uint(v[15]))
         : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // hi / lo TF32 parts of 16 values into two TMEM column ranges of this thread's lane
@@ -60,7 +61,7 @@ __device__ __forceinline__ void tmem_put_split(uint32_t t_hi, uint32_t t_lo, con
     float hi[16], lo[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xFFFFE000u);
+        hi[i] = tf32_hi(v[i]);
         lo[i] = v[i] - hi[i];
     }
     tmem_st16_nowait(t_hi, hi);
@@ -129,24 +130,30 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
         fence_mbar_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
-    // transposed weights as B operands (row = output column n, K = gate / feature index k), hi / lo parts
-    for (int i = tid; i < L::WROWS * D; i += kThreads) {
-        const int row = i / D, k = i % D;
-        float v;
-        if (row < 4 * D) {  // T_r, T_z: n < D -> W_ih[gate*D + k][n], else W_hh[gate*D + k][n - D]
-            const int gate = row / (2 * D), n = row % (2 * D);
-            v = n < D ? __ldg(W_ih + (size_t)(gate * D + k) * D + n) : __ldg(W_hh + (size_t)(gate * D + k) * D + (n - D));
-        } else if (row < 5 * D) {
-            v = __ldg(W_ih + (size_t)(2 * D + k) * D + (row - 4 * D));
-        } else if (row < 6 * D) {
-            v = __ldg(W_hh + (size_t)(2 * D + k) * D + (row - 5 * D));
+    // transposed weights as B operands (row = output column n, K = gate / feature index k), hi / lo parts:
+    // 128-bit loads along n (contiguous in the source), scalar stores into the K-major canonical layout
+    for (int i = tid; i < L::WROWS * D / 4; i += kThreads) {
+        const int k = i % D, r4 = (i / D) * 4;   // rows r4 .. r4+3 of the B tile, K index k
+        const float *srcw;
+        if (r4 < 4 * D) {  // T_r, T_z: n < D -> W_ih[gate*D + k][n], else W_hh[gate*D + k][n - D]
+            const int gate = r4 / (2 * D), n = r4 % (2 * D);
+            srcw = n < D ? W_ih + (size_t)(gate * D + k) * D + n : W_hh + (size_t)(gate * D + k) * D + (n - D);
+        } else if (r4 < 5 * D) {
+            srcw = W_ih + (size_t)(2 * D + k) * D + (r4 - 4 * D);
+        } else if (r4 < 6 * D) {
+            srcw = W_hh + (size_t)(2 * D + k) * D + (r4 - 5 * D);
         } else {
-            v = __ldg(W_h + (size_t)k * D + (row - 6 * D));
+            srcw = W_h + (size_t)k * D + (r4 - 6 * D);
         }
-        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        const int o = L::off(row, k >> 2) + (k & 3) * 4;
-        *reinterpret_cast<float *>(smem + L::W_HI + o) = hi;
-        *reinterpret_cast<float *>(smem + L::W_LO + o) = v - hi;
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(srcw));
+        const float v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float hi = tf32_hi(v[e]);
+            const int o = L::off(r4 + e, k >> 2) + (k & 3) * 4;
+            *reinterpret_cast<float *>(smem + L::W_HI + o) = hi;
+            *reinterpret_cast<float *>(smem + L::W_LO + o) = v[e] - hi;
+        }
     }
     for (int i = tid; i < 8 * D; i += kThreads) wsm[i] = w_small ? w_small[i] : 0.f;
     fence_proxy_async();
@@ -164,6 +171,19 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
         const int64_t row = tile * kTcRows + trow;
         const bool live = row < n_nodes;
         const size_t o = (size_t)(live ? row : 0) * D + c0;
+        {   // pull this thread's slices of the CTA's NEXT tile into L2 while this tile is processed: one CTA
+            // per SM and no second tile in flight, so every dependent load below would otherwise pay DRAM latency
+            const int64_t nrow = row + (int64_t)gridDim.x * kTcRows;
+            if (nrow < n_nodes) {
+                const size_t no = (size_t)nrow * D + c0;
+                if (g_hidden) prefetch_l2(g_hidden + no);
+#pragma unroll
+                for (int pl = 0; pl < 6; ++pl) prefetch_l2(saved + pl * plane + no);
+                if (drop_mask) prefetch_l2(drop_mask + no);
+                if (g_small && cq == 0) prefetch_l2(g_small + (size_t)nrow * 8);
+                if (remap && cq == 0) prefetch_l2(remap + nrow);
+            }
+        }
         float gh0d[16];
         {
             float g[16];
@@ -316,22 +336,42 @@ int launch_node_bwd(const float *g_hidden, const float *g_small, const float *w_
 
 // ------------------------------------------------------------------------------------------------
 // weight gradients: reductions over nodes on CUDA cores
+//
+// Every source (x_act, dropout mask, h0, agg, hidden, G4, g_pre, g_small) is row-major with the node
+// as the row, so the rows of a 16-node slab are ONE contiguous run per source: a slab is staged with
+// up to 8 TMA bulk copies (cp.async.bulk, completion on an mbarrier) issued by one thread into a
+// 3-deep ring; no thread spends registers or issue slots on the loads, and the copy of slab s+2
+// overlaps the FMAs of slab s.  Each thread owns an 8 x 8 register tile of one product space.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWgNodes = 32;   // nodes per shared-memory slab
+constexpr int kWgNodes = 16;   // nodes per ring stage
+constexpr int kWgStages = 3;
 constexpr int kWgCtas = 148 * 2;
 
 template <int D>
 struct Wg {
-    static constexpr int XW = 4 * D;        // x_in | h0 | agg | hidden
-    static constexpr int GW = 5 * D + 8;    // G4 (4D) | g_pre (D) | g_small (8)
+    static constexpr int KS = kWgNodes;
+    // float offsets of the sources inside one ring stage
+    static constexpr int OX = 0, OM = KS * D, OH = 2 * KS * D, OA = 3 * KS * D, OHID = 4 * KS * D, OG4 = 5 * KS * D,
+                         OGP = 9 * KS * D, OGS = 10 * KS * D;
+    static constexpr int STAGE = KS * (10 * D + 8);   // floats
     static constexpr int T1 = (D / 8) * (3 * D / 8), T3 = (D / 8) * (D / 8), T4 = D / 8, T5 = 4 * D / 8;
     static constexpr int TILES = 2 * T1 + T3 + T4 + T5;
     static constexpr int THREADS = ((TILES + 31) / 32) * 32;
     // output layout
     static constexpr int O_WIH = 0, O_WHH = 3 * D * D, O_WH = 6 * D * D, O_WS = 7 * D * D, O_B = 7 * D * D + 8 * D;
     static constexpr int OUT = O_B + 4 * D;
-    static constexpr int SMEM = kWgNodes * (XW + GW) * 4;
+    static constexpr int SMEM = kWgStages * STAGE * 4 + 64;   // + mbarriers
 };
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 
 template <int D, bool HAS_H0>
 __global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
@@ -340,96 +380,128 @@ __global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
     const float *__restrict__ g_pre, const float *__restrict__ g_small, int64_t n_nodes_host,
     const int64_t *__restrict__ n_nodes_dev, float *__restrict__ partial) {
     using W = Wg<D>;
-    extern __shared__ __align__(16) float wg_smem[];
-    float *Xs = wg_smem, *Gs = wg_smem + kWgNodes * W::XW;
+    extern __shared__ __align__(128) float wg_smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(wg_smem + kWgStages * W::STAGE);
     const int tid = threadIdx.x;
     const int64_t n_nodes = n_nodes_dev ? *n_nodes_dev : n_nodes_host;
     const int64_t n_slabs = (n_nodes + kWgNodes - 1) / kWgNodes;
+    const int64_t my_slabs = n_slabs > (int64_t)blockIdx.x ? (n_slabs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const bool has_mask = drop_mask != nullptr, has_small = g_small != nullptr;
 
-    // this thread's 8 x 8 tile: xo / go = float offsets into a node's X / G row, out = first output element,
-    // kind 0 = outer product (out[j * D + i]), 1 = column sums (out[j]), 2 = idle
-    int xo = 0, go = 0, out = 0, kind = 2;
+    // this thread's 8 x 8 tile: xo / go = float offsets inside a ring stage (row strides xs / gs),
+    // out = first output element; kind 0 = outer product (out[j * D + i]), 1 = column sums, 2 = idle
+    int xo = 0, go = 0, gs = 4 * D, mo = -1, out = 0, kind = 2;
     {
         constexpr int IB = D / 8;
         int t = tid;
         if (t < W::T1) {
-            xo = 8 * (t % IB), go = 8 * (t / IB), out = W::O_WIH + go * D + xo, kind = 0;
+            xo = W::OX + 8 * (t % IB), go = W::OG4 + 8 * (t / IB), out = W::O_WIH + 8 * (t / IB) * D + 8 * (t % IB), kind = 0;
+            if (has_mask) mo = W::OM + 8 * (t % IB);
         } else if ((t -= W::T1) < W::T1) {
             const int jc = 8 * (t / IB);
-            xo = D + 8 * (t % IB), go = jc < 2 * D ? jc : jc + D;  // gates r, z, then g_n * r (fourth block of G4)
+            xo = W::OH + 8 * (t % IB), go = W::OG4 + (jc < 2 * D ? jc : jc + D);  // gates r, z, then g_n * r
             out = W::O_WHH + jc * D + 8 * (t % IB), kind = HAS_H0 ? 0 : 2;
         } else if ((t -= W::T1) < W::T3) {
-            xo = 2 * D + 8 * (t % IB), go = 4 * D + 8 * (t / IB), out = W::O_WH + 8 * (t / IB) * D + 8 * (t % IB), kind = 0;
+            xo = W::OA + 8 * (t % IB), go = W::OGP + 8 * (t / IB), gs = D;
+            out = W::O_WH + 8 * (t / IB) * D + 8 * (t % IB), kind = 0;
         } else if ((t -= W::T3) < W::T4) {
-            xo = 3 * D + 8 * t, go = 5 * D, out = W::O_WS + 8 * t, kind = g_small ? 0 : 2;
+            xo = W::OHID + 8 * t, go = W::OGS, gs = 8, out = W::O_WS + 8 * t, kind = has_small ? 0 : 2;
         } else if ((t -= W::T4) < W::T5) {
-            go = 8 * t, out = W::O_B + 8 * t, kind = 1;
+            go = W::OG4 + 8 * t, out = W::O_B + 8 * t, kind = 1;
         }
     }
+    if (tid == 0) {
+        for (int s = 0; s < kWgStages; ++s) mbar_init(full + s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const size_t plane = (size_t)plane_rows * D;
+    auto issue = [&](int64_t it) {   // thread 0: TMA bulk copies of this CTA's it-th slab into ring stage it % kWgStages
+        const int s = (int)(it % kWgStages);
+        float *st = wg_smem + s * W::STAGE;
+        const int64_t base = ((int64_t)blockIdx.x + it * gridDim.x) * kWgNodes;
+        const int64_t left = n_nodes_host - base;    // rows that exist in the buffers (in-bounds copy)
+        const uint32_t rows = (uint32_t)(left < kWgNodes ? left : kWgNodes);
+        const uint32_t rb = rows * D * 4;
+        uint32_t total = rb * 3 + rows * 4 * D * 4;                       // x_act, agg, g_pre, G4
+        if (has_mask) total += rb;
+        if (HAS_H0) total += rb;
+        if (has_small) total += rb + rows * 32;
+        mbar_expect_tx(full + s, total);
+        bulk_g2s(st + W::OX, saved + (size_t)base * D, rb, full + s);
+        if (has_mask) bulk_g2s(st + W::OM, drop_mask + (size_t)base * D, rb, full + s);
+        if (HAS_H0) bulk_g2s(st + W::OH, saved + 5 * plane + (size_t)base * D, rb, full + s);
+        bulk_g2s(st + W::OA, agg + (size_t)base * D, rb, full + s);
+        bulk_g2s(st + W::OG4, G4 + (size_t)base * 4 * D, rows * 4 * D * 4, full + s);
+        bulk_g2s(st + W::OGP, g_pre + (size_t)base * D, rb, full + s);
+        if (has_small) {
+            bulk_g2s(st + W::OHID, hidden + (size_t)base * D, rb, full + s);
+            bulk_g2s(st + W::OGS, g_small + (size_t)base * 8, rows * 32, full + s);
+        }
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < kWgStages && it < my_slabs; ++it) issue(it);
+
     float acc[8][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
 
-    const size_t plane = (size_t)plane_rows * D;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
-        const int64_t base = slab * kWgNodes;
-        __syncthreads();  // the previous slab has been consumed
-        constexpr int D4 = D / 4;
-        for (int i = tid; i < kWgNodes * D4; i += W::THREADS) {  // D-wide sources, one float4 each
-            const int k = i / D4, c = i % D4;
-            const int64_t row = base + k;
-            const bool ok = row < n_nodes;
-            const size_t o = (size_t)(ok ? row : 0) * D + 4 * c;
-            float4 x = ok ? __ldg(reinterpret_cast<const float4 *>(saved + o)) : zero4;
-            if (drop_mask && ok) {
-                const float4 m = __ldg(reinterpret_cast<const float4 *>(drop_mask + o));
-                x = make_float4(x.x * m.x, x.y * m.y, x.z * m.z, x.w * m.w);
-            }
-            float4 *xr = reinterpret_cast<float4 *>(Xs + k * W::XW);
-            xr[c] = x;
-            xr[D4 + c] = (HAS_H0 && ok) ? __ldg(reinterpret_cast<const float4 *>(saved + 5 * plane + o)) : zero4;
-            xr[2 * D4 + c] = ok ? __ldg(reinterpret_cast<const float4 *>(agg + o)) : zero4;
-            xr[3 * D4 + c] = (g_small && ok) ? __ldg(reinterpret_cast<const float4 *>(hidden + o)) : zero4;
-            float4 *gr = reinterpret_cast<float4 *>(Gs + k * W::GW);
-            gr[4 * D4 + c] = ok ? __ldg(reinterpret_cast<const float4 *>(g_pre + o)) : zero4;
-        }
-        for (int i = tid; i < kWgNodes * D; i += W::THREADS) {  // G4: 4D wide
-            const int k = i / D, c = i % D;
-            const int64_t row = base + k;
-            reinterpret_cast<float4 *>(Gs + k * W::GW)[c] =
-                row < n_nodes ? __ldg(reinterpret_cast<const float4 *>(G4 + (size_t)row * 4 * D) + c) : zero4;
-        }
-        for (int i = tid; i < kWgNodes * 2; i += W::THREADS) {  // g_small: 8 wide
-            const int k = i >> 1, c = i & 1;
-            const int64_t row = base + k;
-            reinterpret_cast<float4 *>(Gs + k * W::GW + 5 * D)[c] =
-                (g_small && row < n_nodes) ? __ldg(reinterpret_cast<const float4 *>(g_small + (size_t)row * 8) + c) : zero4;
-        }
-        __syncthreads();
+    for (int64_t it = 0; it < my_slabs; ++it) {
+        const int s = (int)(it % kWgStages);
+        const float *st = wg_smem + s * W::STAGE;
+        const int64_t base = ((int64_t)blockIdx.x + it * gridDim.x) * kWgNodes;
+        const int rows = (int)(n_nodes - base < kWgNodes ? n_nodes - base : kWgNodes);   // true rows only
+        mbar_wait(full + s, (uint32_t)((it / kWgStages) & 1));
         if (kind == 0) {
+            const float *xp = st + xo, *gp = st + go;
+            if (mo >= 0) {
+                const float *mp = st + mo;
+                for (int k = 0; k < rows; ++k) {
+                    const float4 x0 = *reinterpret_cast<const float4 *>(xp + k * D);
+                    const float4 x1 = *reinterpret_cast<const float4 *>(xp + k * D + 4);
+                    const float4 m0 = *reinterpret_cast<const float4 *>(mp + k * D);
+                    const float4 m1 = *reinterpret_cast<const float4 *>(mp + k * D + 4);
+                    const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gs);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gs + 4);
+                    const float xv[8] = {x0.x * m0.x, x0.y * m0.y, x0.z * m0.z, x0.w * m0.w,
+                                         x1.x * m1.x, x1.y * m1.y, x1.z * m1.z, x1.w * m1.w};
+                    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(gv[j], xv[i], acc[j][i]);
+                }
+            } else {
 #pragma unroll 4
-            for (int k = 0; k < kWgNodes; ++k) {
-                const float4 x0 = *reinterpret_cast<const float4 *>(Xs + k * W::XW + xo);
-                const float4 x1 = *reinterpret_cast<const float4 *>(Xs + k * W::XW + xo + 4);
-                const float4 g0 = *reinterpret_cast<const float4 *>(Gs + k * W::GW + go);
-                const float4 g1 = *reinterpret_cast<const float4 *>(Gs + k * W::GW + go + 4);
-                const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                for (int k = 0; k < rows; ++k) {
+                    const float4 x0 = *reinterpret_cast<const float4 *>(xp + k * D);
+                    const float4 x1 = *reinterpret_cast<const float4 *>(xp + k * D + 4);
+                    const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gs);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gs + 4);
+                    const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                    for (int j = 0; j < 8; ++j)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(gv[j], xv[i], acc[j][i]);
+                        for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(gv[j], xv[i], acc[j][i]);
+                }
             }
         } else if (kind == 1) {
-            for (int k = 0; k < kWgNodes; ++k) {
-                const float4 g0 = *reinterpret_cast<const float4 *>(Gs + k * W::GW + go);
-                const float4 g1 = *reinterpret_cast<const float4 *>(Gs + k * W::GW + go + 4);
+            const float *gp = st + go;
+            for (int k = 0; k < rows; ++k) {
+                const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gs);
+                const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gs + 4);
                 acc[0][0] += g0.x; acc[0][1] += g0.y; acc[0][2] += g0.z; acc[0][3] += g0.w;
                 acc[0][4] += g1.x; acc[0][5] += g1.y; acc[0][6] += g1.z; acc[0][7] += g1.w;
             }
+        }
+        __syncthreads();   // every thread is done reading stage s
+        if (tid == 0 && it + kWgStages < my_slabs) {
+            fence_proxy_async();   // generic-proxy reads of the stage are ordered before the async-proxy refill
+            issue(it + kWgStages);
         }
     }
     float *po = partial + (size_t)blockIdx.x * W::OUT + out;
@@ -445,26 +517,34 @@ __global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
     }
 }
 
-// out[o] = sum over CTAs (ascending) of partial[cta][o]; idle tiles' outputs (no h0 / no g_small) are zero
+// out[o] = sum over CTAs of partial[cta][o] in a FIXED order (8 interleaved groups of CTAs, each summed
+// ascending, then a fixed tree over the groups): deterministic, and 8x shorter dependent chains than
+// one thread per output.  Outputs of idle tiles (no h0 / no g_small) are zero.
 template <int D, bool HAS_H0>
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float *__restrict__ partial, int n_ctas, int has_small,
                                                       float *__restrict__ out) {
     using W = Wg<D>;
-    const int o = blockIdx.x * 256 + threadIdx.x;
-    if (o >= W::OUT) return;
-    const bool idle = (!HAS_H0 && o >= W::O_WHH && o < W::O_WH) || (!has_small && o >= W::O_WS && o < W::O_B);
+    __shared__ float sm[8][32];
+    const int ol = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + ol;
     float s = 0.f;
-    if (!idle) {
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-        int c = 0;
-        for (; c + 4 <= n_ctas; c += 4) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) s4[u] += __ldg(partial + (size_t)(c + u) * W::OUT + o);
+    if (o < W::OUT) {
+        const bool idle = (!HAS_H0 && o >= W::O_WHH && o < W::O_WH) || (!has_small && o >= W::O_WS && o < W::O_B);
+        if (!idle) {
+            float s2[2] = {0.f, 0.f};
+            int c = grp;
+            for (; c + 8 < n_ctas; c += 16) {
+                s2[0] += __ldg(partial + (size_t)c * W::OUT + o);
+                s2[1] += __ldg(partial + (size_t)(c + 8) * W::OUT + o);
+            }
+            if (c < n_ctas) s2[0] += __ldg(partial + (size_t)c * W::OUT + o);
+            s = s2[0] + s2[1];
         }
-        for (; c < n_ctas; ++c) s4[0] += __ldg(partial + (size_t)c * W::OUT + o);
-        s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
     }
-    out[o] = s;
+    sm[grp][ol] = s;
+    __syncthreads();
+    if (grp == 0 && o < W::OUT)
+        out[o] = ((sm[0][ol] + sm[1][ol]) + (sm[2][ol] + sm[3][ol])) + ((sm[4][ol] + sm[5][ol]) + (sm[6][ol] + sm[7][ol]));
 }
 
 template <int D, bool HH>
@@ -479,7 +559,7 @@ int launch_wgrad(const float *saved, int64_t plane_rows, const float *drop_mask,
     kern<<<grid, W::THREADS, W::SMEM, st>>>(saved, plane_rows, drop_mask, agg, hidden, G4, g_pre, g_small, n_nodes,
                                            n_nodes_dev, partial);
     RG_LAUNCH_CHECK();
-    k_wgrad_reduce<D, HH><<<(W::OUT + 255) / 256, 256, 0, st>>>(partial, grid, g_small != nullptr, out);
+    k_wgrad_reduce<D, HH><<<(W::OUT + 31) / 32, 256, 0, st>>>(partial, grid, g_small != nullptr, out);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }

@@ -61,6 +61,8 @@ __device__ __forceinline__ float sigmoid_tc(float x) { return __fdividef(1.0f, 1
 __device__ __forceinline__ float tanh_tc(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 // issue the 3xTF32 product  D[tmem_d : N cols] (+)= A(rows 0..127) . B(rows b_row0 .. b_row0+N)^T
+// (a fourth lo.lo term was measured and does not help: on the hub rows of the power-law shape the
+// remaining error comes from the accumulation inside the tensor core, not from the dropped term)
 template <int D>
 __device__ __forceinline__ void issue_gemm(uint32_t smem_base, int a_hi, int a_lo, int b_row0, int N, uint32_t tmem_d,
                                            bool accumulate_first) {

@@ -79,7 +79,7 @@ class _Heavy(object):
         self.struct = None
         if self.max_chunks > 0 and self.max_nodes > 0:
             i32 = lambda n: torch.empty(n, dtype=torch.int32, device=device)
-            self.counters = torch.zeros(4, dtype=torch.int32, device=device)
+            self.counters = torch.zeros(8, dtype=torch.int32, device=device)
             self.bufs = [i32(self.max_chunks), i32(self.max_chunks), i32(self.max_nodes), i32(self.max_nodes),
                          i32(self.max_nodes)]
             self.partial = torch.empty((self.max_chunks, row_floats), dtype=torch.float32, device=device)

@@ -75,6 +75,18 @@ def assert_close(a, b, rtol=1e-4, tag=""):
         tag, err.item(), scale.item(), (err / scale).item(), rtol)
 
 
+def assert_close_yardstick(a, want64, ref_err32, rtol=1e-4, slack=2.0, tag=""):
+    """Scores at the fp32 noise floor (hub entities: sums over 10^3..10^5 in-edges, activations ~10^3): the
+    bar is `rtol` against the fp64 evaluation of the reference formula, or -- where the reference's OWN fp32
+    evaluation is already that far from fp64 (`ref_err32`, relative to max |score|) -- `slack` times that."""
+    a, b = a.detach().cpu().double(), want64.detach().cpu().double()
+    scale = b.abs().max().clamp_min(1e-30)
+    err = float((a - b).abs().max() / scale)
+    bound = max(rtol, slack * float(ref_err32))
+    assert err <= bound, "%s: rel err %.3e vs fp64 > %.3e (reference fp32 vs fp64: %.3e)" % (tag, err, bound, ref_err32)
+    return err
+
+
 def grad_floor(grads64):
     """Absolute floor for near-zero gradient tensors: 1e-7 x the largest gradient entry of the whole
     model ("rtol 1e-4, looser atol for near-zero entries")."""
