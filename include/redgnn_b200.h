@@ -109,7 +109,10 @@ typedef struct rg_segments {
  * kernels drain the queue themselves (idle warps take chunks while others still work on segments);
  * the other variants run a second kernel over it. */
 #ifndef RG_HEAVY_CHUNK
-#define RG_HEAVY_CHUNK 256
+#define RG_HEAVY_CHUNK 256        /* rg_edge_agg_fwd */
+#endif
+#ifndef RG_HEAVY_CHUNK_BWD
+#define RG_HEAVY_CHUNK_BWD 512    /* rg_edge_agg_bwd (measured: 256 costs the backward +10 %) */
 #endif
 typedef struct rg_heavy {
     int32_t max_chunks;
@@ -276,15 +279,6 @@ int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_row
                     const float *g_hidden, const float *saved, float *g_gi, float *g_gh, float *g_h0_direct,
                     float *bias_partial /* optional [ceil(n/64)][4][D]: per-CTA column sums of g_r, g_z, g_n, g_n*r */,
                     void *stream);
-
-/* Stale-row hygiene for shape-static training buffers (rows sized by an upper bound, true count on
- * the device): zero rows [*n_now_dev, *n_prev_dev) of up to 8 row-major [rows][hidden_dim] float
- * planes (`planes`: HOST array of device pointers), then *n_prev_dev = *n_now_dev.  After every step
- * all rows past the true count are exact zeros, so a diverged step (NaN/Inf rows; the reference
- * survives those by re-randomising NaN parameters, base_model.py:65-69) cannot poison the
- * reductions over node rows of later steps. */
-int rg_zero_stale_rows(int32_t hidden_dim, const int64_t *n_now_dev, int64_t *n_prev_dev,
-                       float *const *planes, int32_t n_planes, void *stream);
 
 /* Glue of the graph-captured training step (all shape-static, true counts read on the device):
  *   rg_gather_scores: backward of rg_scatter_scores, g_node[j] = g_scores_all[b_j][e_j] (0 past n);

@@ -14,6 +14,7 @@ RG_COUNTS_WORDS = 8
 RG_CNT_N_IN, RG_CNT_E, RG_CNT_N_OUT, RG_CNT_ERR = 0, 1, 2, 3
 GRAD_COPIES = int(os.environ.get("REDGNN_GRAD_COPIES", "8"))   # relation-gradient accumulator replicas
 RG_HEAVY_CHUNK = int(os.environ.get("REDGNN_HEAVY_CHUNK", "256"))   # must match the library build (developer A/B only)
+RG_HEAVY_CHUNK_BWD = int(os.environ.get("REDGNN_HEAVY_CHUNK_BWD", "512"))
 
 
 class RgGraph(C.Structure):
@@ -69,7 +70,6 @@ SIGNATURES = {
     "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64, C.c_int64] + [C.c_void_p] * 8),
     "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
     "rg_scatter_rows": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
-    "rg_zero_stale_rows": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "rg_query_sum8": (C.c_int, [C.c_int32] + [C.c_void_p] * 4),
     "rg_filtered_ranks": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 7),
     "rg_scatter_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
@@ -142,6 +142,11 @@ class _Timed(object):
         self.t1.record()
         Stats.timing.append((self.name, self.meta, self.t0, self.t1))
         return False
+
+
+def il_plane_floats(rows, d):
+    """Floats of one lane-interleaved plane of `rows` x d (csrc/rg_tc.cuh: 32-row tiles, 132-float chunks)."""
+    return -(-int(rows) // 32) * (d // 4) * 132
 
 
 def check(rc):

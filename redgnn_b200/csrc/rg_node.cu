@@ -328,44 +328,6 @@ extern "C" int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_
     return RG_OK;
 }
 
-// ---- stale-row hygiene for shape-static (upper-bound) training buffers ----------------------------
-namespace {
-struct ZeroPlanes {
-    float4 *p[8];
-    int n;
-};
-
-__global__ void __launch_bounds__(256) k_zero_stale(ZeroPlanes P, const int64_t *__restrict__ n_now,
-                                                    const int64_t *__restrict__ n_prev, int d4) {
-    const int64_t lo = *n_now, hi = *n_prev;
-    if (hi <= lo) return;
-    const int64_t per = (hi - lo) * d4, total = per * P.n;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int pl = (int)(i / per);
-        P.p[pl][lo * d4 + (i - (int64_t)pl * per)] = z;
-    }
-}
-
-__global__ void k_set_prev(const int64_t *__restrict__ n_now, int64_t *n_prev) { *n_prev = *n_now; }
-}  // namespace
-
-extern "C" int rg_zero_stale_rows(int32_t hidden_dim, const int64_t *n_now_dev, int64_t *n_prev_dev,
-                                  float *const *planes, int32_t n_planes, void *stream) {
-    if (hidden_dim <= 0 || hidden_dim % 4 || !n_now_dev || !n_prev_dev || !planes || n_planes < 1 || n_planes > 8)
-        return RG_ERR_BAD_ARG;
-    ZeroPlanes P;
-    P.n = n_planes;
-    for (int i = 0; i < 8; ++i) P.p[i] = i < n_planes ? reinterpret_cast<float4 *>(planes[i]) : nullptr;
-    for (int i = 0; i < n_planes; ++i)
-        if (!planes[i]) return RG_ERR_BAD_ARG;
-    k_zero_stale<<<148 * 2, 256, 0, (cudaStream_t)stream>>>(P, n_now_dev, n_prev_dev, hidden_dim / 4);
-    RG_LAUNCH_CHECK();
-    k_set_prev<<<1, 1, 0, (cudaStream_t)stream>>>(n_now_dev, n_prev_dev);
-    RG_LAUNCH_CHECK();
-    return RG_OK;
-}
-
 extern "C" int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *partial,
                              void *stream) {
     if (n_query <= 0 || !rows24 || !qinfo || !partial) return RG_ERR_BAD_ARG;

@@ -16,8 +16,9 @@
 //   rg_node_wgrad  (k_node_wgrad, CUDA cores, exact fp32, deterministic): the reductions over NODES
 //       dW_ih = G[r,z,n]^T x_in   dW_hh = G[r,z,nr]^T h0   dW_h = g_pre^T agg   dW_small = g_small^T hidden
 //       bias sums = column sums of G4
-//     as 8x8 register tiles over 16-node slabs staged in shared memory by TMA bulk copies (3-deep
-//     mbarrier ring); per-CTA partials are summed in a fixed order by k_wgrad_reduce (no atomics).
+//     as 8x8 register tiles over 32-node slabs staged in shared memory by TMA bulk copies (mbarrier
+//     ring); per-CTA partials are summed in a fixed order by k_wgrad_reduce (no atomics).
+// saved / G4 / g_pre use the lane-interleaved plane layout of rg_tc.cuh (coalesced for lane == row).
 // Both stop at the device-side node count, so upper-bound (shape-static) buffers cost nothing.
 #include "rg_tc.cuh"
 
@@ -53,7 +54,6 @@ __device__ __forceinline__ void tmem_st16_nowait(uint32_t taddr, const float (&v
           "r"(__float_as_uint(v[15]))
         : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // hi / lo TF32 parts of 16 values into two TMEM column ranges of this thread's lane
@@ -74,6 +74,20 @@ __device__ __forceinline__ void ld16(const float *p, float (&v)[16]) {
         const float4 x = __ldg(reinterpret_cast<const float4 *>(p) + q);
         v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
     }
+}
+// this thread's 16-column slice (chunks 4cq .. 4cq+3) of a row of a lane-interleaved plane
+__device__ __forceinline__ void ld16_il(const float *plane, int64_t row, int cq, int KC, float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 x = __ldg(reinterpret_cast<const float4 *>(plane + il_off(row, 4 * cq + q, KC)));
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+    }
+}
+__device__ __forceinline__ void st16_il(float *plane, int64_t row, int cq, int KC, const float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4 *>(plane + il_off(row, 4 * cq + q, KC)) =
+            make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
 __device__ __forceinline__ void st16(float *p, const float (&v)[16]) {
 #pragma unroll
@@ -165,25 +179,13 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
     // TMEM columns: gate operands [2g D, 2g D + D) hi, [2g D + D, 2g D + 2D) lo for g = r, z, n, nr;
     // accumulators g_x [8D, 9D), g_h0 [9D, 10D); second GEMM: g_pre hi/lo in [0, 2D), g_agg in [2D, 3D)
     uint32_t phase = 0;
-    const size_t plane = (size_t)plane_rows * D;
+    const size_t plane = il_plane_floats(plane_rows, D);      // saved planes, G4 planes: lane-interleaved
+    const size_t gplane = il_plane_floats(n_nodes_host, D);
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row = tile * kTcRows + trow;
         const bool live = row < n_nodes;
         const size_t o = (size_t)(live ? row : 0) * D + c0;
-        {   // pull this thread's slices of the CTA's NEXT tile into L2 while this tile is processed: one CTA
-            // per SM and no second tile in flight, so every dependent load below would otherwise pay DRAM latency
-            const int64_t nrow = row + (int64_t)gridDim.x * kTcRows;
-            if (nrow < n_nodes) {
-                const size_t no = (size_t)nrow * D + c0;
-                if (g_hidden) prefetch_l2(g_hidden + no);
-#pragma unroll
-                for (int pl = 0; pl < 6; ++pl) prefetch_l2(saved + pl * plane + no);
-                if (drop_mask) prefetch_l2(drop_mask + no);
-                if (g_small && cq == 0) prefetch_l2(g_small + (size_t)nrow * 8);
-                if (remap && cq == 0) prefetch_l2(remap + nrow);
-            }
-        }
         float gh0d[16];
         {
             float g[16];
@@ -209,11 +211,11 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
             }
             float r[16], z[16], nn[16], hl[16], h0[16];
             if (live) {
-                ld16(saved + plane + o, r);
-                ld16(saved + 2 * plane + o, z);
-                ld16(saved + 3 * plane + o, nn);
-                ld16(saved + 4 * plane + o, hl);
-                ld16(saved + 5 * plane + o, h0);
+                ld16_il(saved + plane, row, cq, KC, r);
+                ld16_il(saved + 2 * plane, row, cq, KC, z);
+                ld16_il(saved + 3 * plane, row, cq, KC, nn);
+                ld16_il(saved + 4 * plane, row, cq, KC, hl);
+                ld16_il(saved + 5 * plane, row, cq, KC, h0);
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) r[j] = z[j] = nn[j] = hl[j] = h0[j] = 0.f;
@@ -227,12 +229,11 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
                 gnr[j] = gnp[j] * r[j];
                 gh0d[j] = g[j] * z[j];
             }
-            if (live) {
-                float *go = G4 + (size_t)row * 4 * D + c0;
-                st16(go, grp);
-                st16(go + D, gzp);
-                st16(go + 2 * D, gnp);
-                st16(go + 3 * D, gnr);
+            if (live) {   // G4: four lane-interleaved planes [4][il_rows(n)][D]
+                st16_il(G4, row, cq, KC, grp);
+                st16_il(G4 + gplane, row, cq, KC, gzp);
+                st16_il(G4 + 2 * gplane, row, cq, KC, gnp);
+                st16_il(G4 + 3 * gplane, row, cq, KC, gnr);
             }
             tmem_put_split(t_lane + 0 * D + c0, t_lane + 1 * D + c0, grp);
             tmem_put_split(t_lane + 2 * D + c0, t_lane + 3 * D + c0, gzp);
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
         // while the MMAs run: this thread's slice of x_act / dropout mask for the epilogue
         float xa[16], mk[16];
         if (live) {
-            ld16(saved + o, xa);
+            ld16_il(saved, row, cq, KC, xa);
             if (drop_mask) ld16(drop_mask + o, mk);
         }
         mbar_wait(bar, phase);
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
                 }
                 v[j] = gp;
             }
-            if (live) st16(g_pre_out + o, v);
+            if (live) st16_il(g_pre_out, row, cq, KC, v);
             tmem_put_split(t_lane + 0 * D + c0, t_lane + 1 * D + c0, v);
             tmem_wait_st();
         }
@@ -337,30 +338,47 @@ int launch_node_bwd(const float *g_hidden, const float *g_small, const float *w_
 // ------------------------------------------------------------------------------------------------
 // weight gradients: reductions over nodes on CUDA cores
 //
-// Every source (x_act, dropout mask, h0, agg, hidden, G4, g_pre, g_small) is row-major with the node
-// as the row, so the rows of a 16-node slab are ONE contiguous run per source: a slab is staged with
-// up to 8 TMA bulk copies (cp.async.bulk, completion on an mbarrier) issued by one thread into a
-// 3-deep ring; no thread spends registers or issue slots on the loads, and the copy of slab s+2
-// overlaps the FMAs of slab s.  Each thread owns an 8 x 8 register tile of one product space.
+// A slab = one 32-node tile.  Every source is ONE contiguous run of memory per slab: the
+// lane-interleaved planes (x_act, h0, the four G4 planes, g_pre; rg_tc.cuh) because a 32-row tile of
+// them is contiguous by construction, the row-major ones (agg, hidden, dropout mask, g_small) because
+// consecutive rows are.  A slab is therefore staged with up to 11 TMA bulk copies (cp.async.bulk,
+// completion on an mbarrier) issued by one thread into a 2-deep ring: no thread spends registers or
+// issue slots on the loads and the copy of slab s+1 overlaps the FMAs of slab s.  Each thread owns an
+// 8 x 8 register tile of one product space; in shared memory element (row k, col i) sits at
+//   interleaved: ((i / 4) * 32 + k) * 4 + i % 4      row-major: k * width + i.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWgNodes = 16;   // nodes per ring stage
-constexpr int kWgStages = 3;
+constexpr int kWgNodes = 32;   // nodes per ring stage = one lane-interleaved tile
+constexpr int kWgStages = 2;   // 2 x 57 KB per CTA: two CTAs per SM
 constexpr int kWgCtas = 148 * 2;
+
+struct WgLayout {   // float offsets of the sources inside one ring stage (-1 = source absent)
+    int ox, om, oh, oa, ohid, og4, ogp, ogs, stage;
+};
 
 template <int D>
 struct Wg {
     static constexpr int KS = kWgNodes;
-    // float offsets of the sources inside one ring stage
-    static constexpr int OX = 0, OM = KS * D, OH = 2 * KS * D, OA = 3 * KS * D, OHID = 4 * KS * D, OG4 = 5 * KS * D,
-                         OGP = 9 * KS * D, OGS = 10 * KS * D;
-    static constexpr int STAGE = KS * (10 * D + 8);   // floats
     static constexpr int T1 = (D / 8) * (3 * D / 8), T3 = (D / 8) * (D / 8), T4 = D / 8, T5 = 4 * D / 8;
     static constexpr int TILES = 2 * T1 + T3 + T4 + T5;
     static constexpr int THREADS = ((TILES + 31) / 32) * 32;
     // output layout
     static constexpr int O_WIH = 0, O_WHH = 3 * D * D, O_WH = 6 * D * D, O_WS = 7 * D * D, O_B = 7 * D * D + 8 * D;
     static constexpr int OUT = O_B + 4 * D;
-    static constexpr int SMEM = kWgStages * STAGE * 4 + 64;   // + mbarriers
+    static WgLayout layout(bool has_mask, bool has_h0, bool has_small) {
+        WgLayout l;
+        constexpr int IL = il_tile_floats(D);       // one lane-interleaved tile (padded chunks)
+        int o = 0;
+        l.ox = o, o += IL;
+        l.om = has_mask ? o : -1, o += has_mask ? KS * D : 0;
+        l.oh = has_h0 ? o : -1, o += has_h0 ? IL : 0;
+        l.oa = o, o += KS * D;
+        l.ohid = has_small ? o : -1, o += has_small ? KS * D : 0;
+        l.og4 = o, o += 4 * IL;
+        l.ogp = o, o += IL;
+        l.ogs = has_small ? o : -1, o += has_small ? KS * 8 : 0;
+        l.stage = o;
+        return l;
+    }
 };
 
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -374,40 +392,45 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 
 template <int D, bool HAS_H0>
-__global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
+__global__ void __maxnreg__(112) k_node_wgrad(
     const float *__restrict__ saved, int64_t plane_rows, const float *__restrict__ drop_mask,
     const float *__restrict__ agg, const float *__restrict__ hidden, const float *__restrict__ G4,
     const float *__restrict__ g_pre, const float *__restrict__ g_small, int64_t n_nodes_host,
-    const int64_t *__restrict__ n_nodes_dev, float *__restrict__ partial) {
+    const int64_t *__restrict__ n_nodes_dev, float *__restrict__ partial, WgLayout L) {
     using W = Wg<D>;
     extern __shared__ __align__(128) float wg_smem[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(wg_smem + kWgStages * W::STAGE);
+    uint64_t *full = reinterpret_cast<uint64_t *>(wg_smem + kWgStages * L.stage);
     const int tid = threadIdx.x;
     const int64_t n_nodes = n_nodes_dev ? *n_nodes_dev : n_nodes_host;
     const int64_t n_slabs = (n_nodes + kWgNodes - 1) / kWgNodes;
     const int64_t my_slabs = n_slabs > (int64_t)blockIdx.x ? (n_slabs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const bool has_mask = drop_mask != nullptr, has_small = g_small != nullptr;
 
-    // this thread's 8 x 8 tile: xo / go = float offsets inside a ring stage (row strides xs / gs),
+    // this thread's 8 x 8 tile.  x / g operand of node k, half h (4 floats): stage[xo + k * xk + h * xh], likewise g;
     // out = first output element; kind 0 = outer product (out[j * D + i]), 1 = column sums, 2 = idle
-    int xo = 0, go = 0, gs = 4 * D, mo = -1, out = 0, kind = 2;
+    int xo = 0, xk = 4, xh = kIlChunk, go = 0, gk = 4, gh = kIlChunk, mo = -1, out = 0, kind = 2;
     {
         constexpr int IB = D / 8;
+        auto il = [](int base, int col) { return base + (col / 4) * kIlChunk; };   // interleaved: chunk offset, k * 4 added
+        auto g4 = [&](int col) { return il(L.og4 + (col / D) * il_tile_floats(D), col % D); };
         int t = tid;
         if (t < W::T1) {
-            xo = W::OX + 8 * (t % IB), go = W::OG4 + 8 * (t / IB), out = W::O_WIH + 8 * (t / IB) * D + 8 * (t % IB), kind = 0;
-            if (has_mask) mo = W::OM + 8 * (t % IB);
+            xo = il(L.ox, 8 * (t % IB)), go = g4(8 * (t / IB));
+            out = W::O_WIH + 8 * (t / IB) * D + 8 * (t % IB), kind = 0;
+            if (has_mask) mo = L.om + 8 * (t % IB);
         } else if ((t -= W::T1) < W::T1) {
             const int jc = 8 * (t / IB);
-            xo = W::OH + 8 * (t % IB), go = W::OG4 + (jc < 2 * D ? jc : jc + D);  // gates r, z, then g_n * r
+            xo = il(L.oh, 8 * (t % IB)), go = g4(jc < 2 * D ? jc : jc + D);   // gates r, z, then g_n * r (fourth plane)
             out = W::O_WHH + jc * D + 8 * (t % IB), kind = HAS_H0 ? 0 : 2;
         } else if ((t -= W::T1) < W::T3) {
-            xo = W::OA + 8 * (t % IB), go = W::OGP + 8 * (t / IB), gs = D;
+            xo = L.oa + 8 * (t % IB), xk = D, xh = 4;                          // agg: row-major
+            go = il(L.ogp, 8 * (t / IB));
             out = W::O_WH + 8 * (t / IB) * D + 8 * (t % IB), kind = 0;
         } else if ((t -= W::T3) < W::T4) {
-            xo = W::OHID + 8 * t, go = W::OGS, gs = 8, out = W::O_WS + 8 * t, kind = has_small ? 0 : 2;
+            xo = L.ohid + 8 * t, xk = D, xh = 4;                               // hidden, g_small: row-major
+            go = L.ogs, gk = 8, gh = 4, out = W::O_WS + 8 * t, kind = has_small ? 0 : 2;
         } else if ((t -= W::T4) < W::T5) {
-            go = W::OG4 + 8 * t, out = W::O_B + 8 * t, kind = 1;
+            go = g4(8 * t), out = W::O_B + 8 * t, kind = 1;
         }
     }
     if (tid == 0) {
@@ -416,28 +439,33 @@ __global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
     }
     __syncthreads();
 
-    const size_t plane = (size_t)plane_rows * D;
+    const size_t plane = il_plane_floats(plane_rows, D);      // saved planes
+    const size_t gplane = il_plane_floats(n_nodes_host, D);   // G4 planes
     auto issue = [&](int64_t it) {   // thread 0: TMA bulk copies of this CTA's it-th slab into ring stage it % kWgStages
         const int s = (int)(it % kWgStages);
-        float *st = wg_smem + s * W::STAGE;
+        float *st = wg_smem + s * L.stage;
         const int64_t base = ((int64_t)blockIdx.x + it * gridDim.x) * kWgNodes;
-        const int64_t left = n_nodes_host - base;    // rows that exist in the buffers (in-bounds copy)
+        const int64_t left = n_nodes_host - base;    // rows that exist in the ROW-MAJOR buffers (in-bounds copy)
         const uint32_t rows = (uint32_t)(left < kWgNodes ? left : kWgNodes);
+        const uint32_t tb = il_tile_floats(D) * 4;   // a full interleaved tile (planes are padded to 32 rows)
         const uint32_t rb = rows * D * 4;
-        uint32_t total = rb * 3 + rows * 4 * D * 4;                       // x_act, agg, g_pre, G4
+        uint32_t total = tb * 6 + rb;                                     // x_act, 4 x G4, g_pre; agg
         if (has_mask) total += rb;
-        if (HAS_H0) total += rb;
+        if (HAS_H0) total += tb;
         if (has_small) total += rb + rows * 32;
         mbar_expect_tx(full + s, total);
-        bulk_g2s(st + W::OX, saved + (size_t)base * D, rb, full + s);
-        if (has_mask) bulk_g2s(st + W::OM, drop_mask + (size_t)base * D, rb, full + s);
-        if (HAS_H0) bulk_g2s(st + W::OH, saved + 5 * plane + (size_t)base * D, rb, full + s);
-        bulk_g2s(st + W::OA, agg + (size_t)base * D, rb, full + s);
-        bulk_g2s(st + W::OG4, G4 + (size_t)base * 4 * D, rows * 4 * D * 4, full + s);
-        bulk_g2s(st + W::OGP, g_pre + (size_t)base * D, rb, full + s);
+        const size_t toff = (size_t)(base >> 5) * il_tile_floats(D);   // this tile inside an interleaved plane
+        bulk_g2s(st + L.ox, saved + toff, tb, full + s);
+        if (has_mask) bulk_g2s(st + L.om, drop_mask + (size_t)base * D, rb, full + s);
+        if (HAS_H0) bulk_g2s(st + L.oh, saved + 5 * plane + toff, tb, full + s);
+        bulk_g2s(st + L.oa, agg + (size_t)base * D, rb, full + s);
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+            bulk_g2s(st + L.og4 + g * il_tile_floats(D), G4 + g * gplane + toff, tb, full + s);
+        bulk_g2s(st + L.ogp, g_pre + toff, tb, full + s);
         if (has_small) {
-            bulk_g2s(st + W::OHID, hidden + (size_t)base * D, rb, full + s);
-            bulk_g2s(st + W::OGS, g_small + (size_t)base * 8, rows * 32, full + s);
+            bulk_g2s(st + L.ohid, hidden + (size_t)base * D, rb, full + s);
+            bulk_g2s(st + L.ogs, g_small + (size_t)base * 8, rows * 32, full + s);
         }
     };
     if (tid == 0)
@@ -451,7 +479,7 @@ __global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
 
     for (int64_t it = 0; it < my_slabs; ++it) {
         const int s = (int)(it % kWgStages);
-        const float *st = wg_smem + s * W::STAGE;
+        const float *st = wg_smem + s * L.stage;
         const int64_t base = ((int64_t)blockIdx.x + it * gridDim.x) * kWgNodes;
         const int rows = (int)(n_nodes - base < kWgNodes ? n_nodes - base : kWgNodes);   // true rows only
         mbar_wait(full + s, (uint32_t)((it / kWgStages) & 1));
@@ -460,12 +488,12 @@ __global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
             if (mo >= 0) {
                 const float *mp = st + mo;
                 for (int k = 0; k < rows; ++k) {
-                    const float4 x0 = *reinterpret_cast<const float4 *>(xp + k * D);
-                    const float4 x1 = *reinterpret_cast<const float4 *>(xp + k * D + 4);
+                    const float4 x0 = *reinterpret_cast<const float4 *>(xp + k * xk);
+                    const float4 x1 = *reinterpret_cast<const float4 *>(xp + k * xk + xh);
                     const float4 m0 = *reinterpret_cast<const float4 *>(mp + k * D);
                     const float4 m1 = *reinterpret_cast<const float4 *>(mp + k * D + 4);
-                    const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gs);
-                    const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gs + 4);
+                    const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gk);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gk + gh);
                     const float xv[8] = {x0.x * m0.x, x0.y * m0.y, x0.z * m0.z, x0.w * m0.w,
                                          x1.x * m1.x, x1.y * m1.y, x1.z * m1.z, x1.w * m1.w};
                     const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -477,10 +505,10 @@ __global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
             } else {
 #pragma unroll 4
                 for (int k = 0; k < rows; ++k) {
-                    const float4 x0 = *reinterpret_cast<const float4 *>(xp + k * D);
-                    const float4 x1 = *reinterpret_cast<const float4 *>(xp + k * D + 4);
-                    const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gs);
-                    const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gs + 4);
+                    const float4 x0 = *reinterpret_cast<const float4 *>(xp + k * xk);
+                    const float4 x1 = *reinterpret_cast<const float4 *>(xp + k * xk + xh);
+                    const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gk);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gk + gh);
                     const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                     const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
@@ -492,8 +520,8 @@ __global__ void __launch_bounds__(Wg<D>::THREADS, 2) k_node_wgrad(
         } else if (kind == 1) {
             const float *gp = st + go;
             for (int k = 0; k < rows; ++k) {
-                const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gs);
-                const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gs + 4);
+                const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gk);
+                const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gk + gh);
                 acc[0][0] += g0.x; acc[0][1] += g0.y; acc[0][2] += g0.z; acc[0][3] += g0.w;
                 acc[0][4] += g1.x; acc[0][5] += g1.y; acc[0][6] += g1.z; acc[0][7] += g1.w;
             }
@@ -552,12 +580,14 @@ int launch_wgrad(const float *saved, int64_t plane_rows, const float *drop_mask,
                  const float *G4, const float *g_pre, const float *g_small, int64_t n_nodes, const int64_t *n_nodes_dev,
                  float *partial, float *out, cudaStream_t st) {
     using W = Wg<D>;
+    const WgLayout L = W::layout(drop_mask != nullptr, HH, g_small != nullptr);
+    const size_t smem = (size_t)kWgStages * L.stage * 4 + 64;   // + mbarriers
     auto kern = k_node_wgrad<D, HH>;
-    RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM));
+    RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_slabs = rg_cdiv(n_nodes, kWgNodes);
     const int grid = (int)(n_slabs < kWgCtas ? n_slabs : kWgCtas);
-    kern<<<grid, W::THREADS, W::SMEM, st>>>(saved, plane_rows, drop_mask, agg, hidden, G4, g_pre, g_small, n_nodes,
-                                           n_nodes_dev, partial);
+    kern<<<grid, W::THREADS, smem, st>>>(saved, plane_rows, drop_mask, agg, hidden, G4, g_pre, g_small, n_nodes, n_nodes_dev,
+                                        partial, L);
     RG_LAUNCH_CHECK();
     k_wgrad_reduce<D, HH><<<(W::OUT + 31) / 32, 256, 0, st>>>(partial, grid, g_small != nullptr, out);
     RG_LAUNCH_CHECK();

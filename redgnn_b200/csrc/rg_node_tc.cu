@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                        hi, lo;
                 if (live) {  // training: keep x_act for the backward pass, apply the (scaled) dropout mask
                     const size_t o = (size_t)row * D + c0 + 4 * q;
-                    if (saved) *reinterpret_cast<float4 *>(saved + o) = x;
+                    if (saved) *reinterpret_cast<float4 *>(saved + il_off(row, c0 / 4 + q, KC)) = x;
                     if (drop_mask) {
                         const float4 mk = __ldg(reinterpret_cast<const float4 *>(drop_mask + o));
                         x = make_float4(x.x * mk.x, x.y * mk.y, x.z * mk.z, x.w * mk.w);
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
                     hn[j] = (1.0f - zg) * ng + zg * h0v[j];
                     sv[0][e] = rg; sv[1][e] = zg; sv[2][e] = ng; sv[3][e] = hlin;
                 }
-                if (saved && live) {  // planes 1..5 of saved[6][n][D], 128-bit stores
-                    const size_t plane = (size_t)n_nodes_host * D, o = (size_t)row * D + c0 + 4 * q;
+                if (saved && live) {  // planes 1..5 of saved[6][il_plane_floats(n, D)] (lane-interleaved, rg_tc.cuh)
+                    const size_t plane = il_plane_floats(n_nodes_host, D), o = il_off(row, c0 / 4 + q, KC);
 #pragma unroll
                     for (int pl = 0; pl < 4; ++pl)
                         *reinterpret_cast<float4 *>(saved + (pl + 1) * plane + o) =

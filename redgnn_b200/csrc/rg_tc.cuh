@@ -112,6 +112,24 @@ __device__ __forceinline__ void split_tf32(float4 x, float4 &hi, float4 &lo) {
     lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
 }
 
+// "Lane-interleaved" plane layout of the buffers that only the tensor-core node kernels exchange (the
+// saved gate planes, G4, g_pre): rows in tiles of 32, inside a tile chunk-major,
+//     [tile = row / 32][chunk = col / 4][row % 32][4 floats]  (+ 4 pad floats per chunk).
+// In those kernels lane == node row (TMEM lane), so with row-major rows of 4*D bytes every 128-bit load /
+// store instruction of a warp touched 32 different cache lines (ncu: the LSU wavefront pipe was the top
+// limiter of k_node_bwd_tc at 56 %); here the 32 lanes of one instruction cover 512 contiguous bytes.
+// A 32-row tile is still ONE contiguous run of kIlTile(D) floats (what the weight-gradient kernel
+// bulk-copies into shared memory); the 16-byte pad per chunk staggers the chunks over the shared-memory
+// banks there (unpadded, all chunks of a row sit 512 B apart = on the same banks).
+constexpr int kIlChunk = 132;                                                     // floats per chunk of a tile
+__host__ __device__ constexpr int il_tile_floats(int D) { return (D / 4) * kIlChunk; }
+__host__ __device__ __forceinline__ size_t il_plane_floats(int64_t rows, int D) {
+    return (size_t)((rows + 31) >> 5) * il_tile_floats(D);
+}
+__device__ __forceinline__ size_t il_off(int64_t row, int chunk, int chunks_per_row) {
+    return ((size_t)(row >> 5) * chunks_per_row + chunk) * kIlChunk + (size_t)(row & 31) * 4;   // in floats
+}
+
 // D[tmem] (+)= A[tmem: lane = row, 8 consecutive 32-bit columns = K] . B[smem]^T ; one K=8 TF32 slice
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                                uint32_t accumulate) {

@@ -88,9 +88,9 @@ class DeviceGraph(object):
         """Per-query upper bounds (chunks, nodes) for the heavy-segment queues of the edge kernels.
         Captured CUDA graphs have queue buffers of these sizes baked in, so an in-place rebuild only
         ever GROWS them (with 10 % headroom) and bumps `epoch`, which is part of the capture keys."""
-        ck = _lib.RG_HEAVY_CHUNK
+        ck, ckb = _lib.RG_HEAVY_CHUNK, _lib.RG_HEAVY_CHUNK_BWD     # forward pulls in-edges, backward pushes out-edges
         stats = torch.stack([((in_deg - 1) // ck).sum(), (in_deg > ck).sum(),
-                             ((out_deg - 1) // ck).sum(), (out_deg > ck).sum()]).cpu().tolist()
+                             ((out_deg - 1) // ckb).sum(), (out_deg > ckb).sum()]).cpu().tolist()
         exact_in, exact_out = (int(stats[0]), int(stats[1])), (int(stats[2]), int(stats[3]))
         if not grow_only:
             self.heavy_in, self.heavy_out = exact_in, exact_out

@@ -72,7 +72,8 @@ class GNNLayer(torch.nn.Module):
             return self.act(self.W_h(torch.zeros((int(n_node), self.in_dim), device=hidden.device)))
         sub, rel, obj, r_idx = edges[:, 4], edges[:, 2], edges[:, 5], edges[:, 0]
         fwd_seg = Segments.explicit(obj, sub, rel, r_idx, int(n_node))
-        bwd_seg = Segments.explicit(sub, obj, rel, r_idx, int(hidden.shape[0])) if torch.is_grad_enabled() else None
+        bwd_seg = Segments.explicit(sub, obj, rel, r_idx, int(hidden.shape[0]), backward=True) \
+            if torch.is_grad_enabled() else None
         return self.propagate(q_rel, hidden, fwd_seg, bwd_seg)
 
 

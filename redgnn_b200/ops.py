@@ -39,9 +39,10 @@ class Segments(object):
         return seg
 
     @staticmethod
-    def explicit(seg_index, peer_index, rel, query, n_seg):
+    def explicit(seg_index, peer_index, rel, query, n_seg, backward=False):
         """Group an arbitrary edge list by `seg_index` (stable, so the in-segment order is the
-        caller's edge order).  All arguments are int64 cuda tensors of length E."""
+        caller's edge order).  All arguments are int64 cuda tensors of length E.  `backward`: the
+        segments feed rg_edge_agg_bwd (its heavy-segment chunk size differs)."""
         order = torch.sort(seg_index, stable=True)[1]
         deg = torch.bincount(seg_index, minlength=n_seg)
         seg_ptr = torch.zeros(n_seg + 1, dtype=torch.int64, device=seg_index.device)
@@ -49,7 +50,7 @@ class Segments(object):
         adj = torch.stack([peer_index[order], rel[order]], dim=1).to(torch.int32).contiguous()
         seg_query = torch.zeros(n_seg, dtype=torch.int32, device=seg_index.device)
         seg_query[seg_index] = query.to(torch.int32)
-        ck = _lib.RG_HEAVY_CHUNK
+        ck = _lib.RG_HEAVY_CHUNK_BWD if backward else _lib.RG_HEAVY_CHUNK
         if deg.numel():
             bound = (int(((deg - 1).clamp_(min=0) // ck).sum()), int((deg > ck).sum()))
         else:
@@ -191,7 +192,7 @@ class NodeUpdateTrain(torch.autograd.Function):
                                                                              b_hh, mask))
         n, d = agg.shape
         hidden = torch.empty((n, d), dtype=torch.float32, device=agg.device)
-        saved = torch.empty((6, n, d), dtype=torch.float32, device=agg.device)
+        saved = torch.empty((6, _lib.il_plane_floats(n, d)), dtype=torch.float32, device=agg.device)   # lane-interleaved
         with _lib.Stats.timed("node_update_train", (n, d)):
             check(lib.rg_node_update_train(d, n, None, ptr(agg), ptr(h_prev), ptr(src), ptr(W_h), ptr(w_ih), ptr(w_hh),
                                            ptr(b_ih), ptr(b_hh), act_code, ptr(mask), ptr(hidden), ptr(saved),
@@ -209,7 +210,8 @@ class NodeUpdateTrain(torch.autograd.Function):
         dev = agg.device
         g_h = g_h.to(torch.float32).contiguous()
         e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-        G4, g_pre, g_agg = e(n, 4 * d), e(n, d), e(n, d)
+        pl = _lib.il_plane_floats(n, d)
+        G4, g_pre, g_agg = e(4, pl), e(pl), e(n, d)
         g_h0 = e(n, d) if ctx.has_h0 else None
         mk = mask if ctx.has_mask else None
         with _lib.Stats.timed("node_bwd", (n, d)):

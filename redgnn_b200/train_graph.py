@@ -9,13 +9,11 @@ backward, tensor-core node backward, weight-gradient reduction kernel), and both
 once as CUDA graphs.  A single torch.autograd.Function replays them, so `loss.backward()` and the
 optimiser in the caller's loop (Static/*/base_model.py:49-70) work unchanged.
 
-Invariant that makes upper-bound buffers safe: after every forward replay each persistent per-node
-buffer (agg, hidden, the saved gate planes) is an exact zero in every row past that step's true node
-count -- the buffers start as zeros, the kernels write rows below the count only, and
-rg_zero_stale_rows clears the rows a larger previous step left behind (so even a diverged step,
-which the reference loop survives by re-randomising NaN parameters, base_model.py:65-69, cannot leak
-NaN/Inf into later steps); every gradient row past the true count is an exact zero as well
-(rg_gru_bwd_elem / rg_gather_scores write zeros there, node_small is cleared per replay).
+Invariant that makes upper-bound buffers safe: EVERY consumer of a per-node buffer (edge kernels,
+node update, node backward, weight-gradient reduction, score scatter / gather, per-query sums) reads
+the true node count from device memory and never touches a row past it, so stale rows -- including
+NaN/Inf rows a diverged step left behind, which the reference loop survives by re-randomising NaN
+parameters, base_model.py:65-69 -- are simply never read (tests/test_robustness_gpu.py injects one).
 
 Forward and backward both run on the full upper-bound buffers and every kernel stops at the
 device-side node count, so there is ONE captured forward and ONE captured backward per runner and no
@@ -64,12 +62,13 @@ class TrainStepRunner(object):
         # persistent, finite-by-construction buffers (see module docstring)
         self.agg = [z(self.cap, self.d) for _ in range(self.n_layer)]
         self.hidden = [z(self.cap, self.d) for _ in range(self.n_layer)]
-        self.saved = [z(6, self.cap, self.d) for _ in range(self.n_layer)]
+        # saved gate planes / G4 / g_pre: lane-interleaved planes (csrc/rg_tc.cuh)
+        self.plane = _lib.il_plane_floats(self.cap, self.d)
+        self.saved = [z(6, self.plane) for _ in range(self.n_layer)]
         self.as8 = [z(self.cap, 8) for _ in range(self.n_layer - 1)]       # next layer's Ws_attn(hidden), per node
         self.score_node = z(self.cap)
         self.wg_out_floats = int(lib.rg_node_wgrad_out_floats(self.d))
         self.wg_partial = torch.empty(int(lib.rg_node_wgrad_ctas()) * self.wg_out_floats, dtype=torch.float32, device=dev)
-        self.prev_n = torch.zeros(self.n_layer, dtype=torch.int64, device=dev)   # true node counts of the previous replay
         self.ws = graph.workspace(self.n)      # keeps the expansion scratch the captured graphs point at alive
         self.kg_epoch = graph.epoch
         self.L = None
@@ -86,7 +85,9 @@ class TrainStepRunner(object):
         batch = torch.arange(n, device=dev)
         fr = g.frontier_from_nodes(torch.stack([batch, q_sub], dim=1), n)
         self.fr0 = fr
-        node_b, node_e = batch.to(torch.int32), q_sub.to(torch.int32)
+        # (an out-of-range subject is dropped by the frontier kernels and flagged in RG_CNT_ERR; clamped here so
+        # that the layer-0 backward segments, which index the CSR by it, stay in bounds)
+        node_b, node_e = batch.to(torch.int32), q_sub.clamp(0, g.n_ent - 1).to(torch.int32)
         onehot = torch.zeros((n, 2 * m.n_rel + 1), dtype=torch.float32, device=dev)
         onehot.scatter_(1, q_rel[:, None], 1.0)
         hidden, n_in_dev, L = None, None, []
@@ -132,10 +133,6 @@ class TrainStepRunner(object):
                                            ptr(m.W_final.weight) if last else None,
                                            ptr(self.as8[i]) if not last else None,
                                            ptr(self.score_node) if last else None, stream_ptr()))
-            planes = (C.c_void_p * 8)(self.agg[i].data_ptr(), self.hidden[i].data_ptr(),
-                                      *[self.saved[i][k].data_ptr() for k in range(6)])
-            check(lib.rg_zero_stale_rows(d, ptr(n_dev), ptr(self.prev_n[i:i + 1]), planes, 8, stream_ptr()))
-            _lib.Stats.launches += 2
             L.append(dict(fr_in=fr, fr_out=fr_next, n_dev=n_dev, nb=nb, ne=ne, src=src, remap=remap, ws_next=ws_next,
                           rela=rela, Ws8=Ws8, Wr8=Wr8,
                           Wqr8=Wqr8, w8=w8, ar8=ar8, hq=hq, aq8=aq8, as8=as8, hidden_prev=hidden, mask=mask,
@@ -180,7 +177,7 @@ class TrainStepRunner(object):
             lay, layer = self.L[i], m.gnn_layers[i]
             pre = "gnn_layers.%d." % i
             has_h0 = lay["hidden_prev"] is not None
-            G4, g_pre, g_agg = e(cap, 4 * d), e(cap, d), e(cap, d)
+            G4, g_pre, g_agg = e(4, self.plane), e(self.plane), e(cap, d)
             g_h0 = e(cap, d) if has_h0 else None
             check(lib.rg_node_bwd(d, cap, ptr(lay["n_dev"]), ptr(g_hid_e), ptr(g_small), ptr(w_small), ptr(g_h0_next),
                                   ptr(remap), ptr(self.saved[i]), cap, ptr(lay["mask"]), ptr(layer.W_h.weight),

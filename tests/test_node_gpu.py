@@ -102,12 +102,13 @@ def test_node_backward_native_kernels_vs_fp64_autograd(d, n, act, has_h0, drop, 
     remap = torch.randperm(n_next, device=dev)[:n].sort()[0].to(torch.int32) if fold else None
     # forward through the training kernel (saves the gates)
     hidden = torch.empty(n, d, device=dev)
-    saved = torch.empty(6, n, d, device=dev)
+    pl = _lib.il_plane_floats(n, d)               # saved / G4 / g_pre: lane-interleaved planes (csrc/rg_tc.cuh)
+    saved = torch.empty(6, pl, device=dev)
     check(lib.rg_node_update_train(d, n, None, ptr(agg), ptr(h_prev), ptr(src), ptr(W_h), ptr(gru.weight_ih_l0),
                                    ptr(gru.weight_hh_l0), ptr(gru.bias_ih_l0), ptr(gru.bias_hh_l0), act, ptr(mask),
                                    ptr(hidden), ptr(saved), None, None, None, None, stream_ptr()))
     e = lambda *s: torch.empty(*s, device=dev)
-    G4, g_pre, g_agg, g_h0 = e(n, 4 * d), e(n, d), e(n, d), (e(n, d) if has_h0 else None)
+    G4, g_pre, g_agg, g_h0 = e(4, pl), e(pl), e(n, d), (e(n, d) if has_h0 else None)
     check(lib.rg_node_bwd(d, n, None, ptr(g_hidden), ptr(g_small), ptr(w_small), ptr(g_h0_next), ptr(remap), ptr(saved), n,
                           ptr(mask), ptr(W_h), ptr(gru.weight_ih_l0), ptr(gru.weight_hh_l0), act, int(has_h0), ptr(G4),
                           ptr(g_pre), ptr(g_agg), ptr(g_h0), stream_ptr()))
