@@ -243,12 +243,13 @@ int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_n
                          const float *agg, const float *h_prev,
                          const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                          const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
-                         float *hidden, float *saved, const float *Ws_next, const float *W_final,
-                         float *as8, float *score, void *stream);
+                         float *hidden, float *saved, const float *Ws_next, int32_t ws_rows,
+                         const float *W_final, float *as8, float *score, void *stream);
 
 /* Training BACKWARD of the node update (autograd of models.py:41,81-84), dense part, native:
  * rg_node_bwd (tensor cores, hidden_dim <= 48), per node row j < n_nodes:
- *   g      = g_hidden[j] (+ g_small[j][0..7] . w_small[8][D]) (+ g_h0_next[remap[j]])      upstream
+ *   g      = g_hidden[j] (+ g_small[j][0..w_small_rows) . w_small[w_small_rows][D]) (+ g_h0_next[remap[j]])
+ *            (g_small rows are g_small_stride floats apart: 8, or 24 for rg_edge_agg_bwd's node_small)
  *   G4[j]  = [g_r' | g_z' | g_n' | g_n' r]     gradients of the GRU gate pre-activations ([n][4D])
  *   g_pre[j] = ([g_r' g_z' g_n'] . W_ih) * drop_mask * act'(x)
  *   g_agg[j] = g_pre[j] . W_h                                       (input of rg_edge_agg_bwd)
@@ -263,16 +264,38 @@ int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_n
  * dW_small = g_small^T hidden.  `partial` is scratch of rg_node_wgrad_ctas() * rg_node_wgrad_out_floats()
  * floats (per-CTA partial sums, added in CTA order). */
 int rg_node_bwd(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *g_hidden,
-                const float *g_small, const float *w_small, const float *g_h0_next, const int32_t *remap,
-                const float *saved, int64_t saved_plane_rows, const float *drop_mask, const float *W_h,
-                const float *W_ih, const float *W_hh, int32_t act, int32_t has_h0, float *G4, float *g_pre,
-                float *g_agg, float *g_h0, void *stream);
+                const float *g_small, int32_t g_small_stride, const float *w_small, int32_t w_small_rows,
+                const float *g_h0_next,
+                const int32_t *remap, const float *saved, int64_t saved_plane_rows, const float *drop_mask,
+                const float *W_h, const float *W_ih, const float *W_hh, int32_t act, int32_t has_h0, float *G4,
+                float *g_pre, float *g_agg, float *g_h0, void *stream);
 int32_t rg_node_wgrad_ctas(void);
 int64_t rg_node_wgrad_out_floats(int32_t hidden_dim);
+/* `out` != NULL: the packed vector above.  `out` == NULL: the sums go straight into the parameter
+ * gradients -- g_wih / g_whh / g_bih / g_bhh (GRU, shared by all layers) are ACCUMULATED, g_wh [D][D] and
+ * the first ws_rows rows of the small projection g_ws (may be NULL) are written. */
 int rg_node_wgrad(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *saved,
                   int64_t saved_plane_rows, const float *drop_mask, const float *agg, const float *hidden,
-                  const float *G4, const float *g_pre, const float *g_small, int32_t has_h0, float *partial,
-                  float *out, void *stream);
+                  const float *G4, const float *g_pre, const float *g_small, int32_t g_small_stride, int32_t has_h0,
+                  float *partial, float *out, float *g_wih, float *g_whh, float *g_bih, float *g_bhh, float *g_wh,
+                  float *g_ws, int32_t ws_rows, void *stream);
+
+/* ---- per-relation / per-query side of a layer (models.py:29-36) ----------------------------------
+ * rg_attn_tables: ar8[r] = Wr_attn . rela[r] (n_rows x 8), aq8[b] = Wqr_attn . rela[q_rel[b]] + b_qr
+ * (n_query x 8), w8 = w_alpha padded to 8; columns >= attn_dim are zero.  Weights in the reference's own
+ * shapes (Wr, Wqr: [attn_dim][D]).
+ * rg_attn_param_grads: every parameter gradient of that side from what rg_edge_agg_bwd (g_rela / g_ar8
+ * accumulator copies) and rg_query_sum8 (q_part [n][q_slices][24]) produced, written in place:
+ *   g_rela [n_rows][D] = sum_copies g_rela + g_ar8 . Wr + scatter_b(g_aq8[b] . Wqr -> row q_rel[b])
+ *   g_Wr, g_Wqr [attn_dim][D], g_bqr, g_w_alpha [attn_dim], g_b_alpha [1].  Fixed summation order. */
+int rg_attn_tables(int32_t hidden_dim, int32_t attn_dim, int32_t n_rows, int32_t n_query, const float *rela,
+                   const float *Wr, const float *Wqr, const float *bqr, const float *w_alpha,
+                   const int64_t *q_rel, float *ar8, float *aq8, float *w8, void *stream);
+int rg_attn_param_grads(int32_t hidden_dim, int32_t attn_dim, int32_t n_rows, int32_t n_query,
+                        int32_t grad_copies, const float *rela, const float *Wr, const float *Wqr,
+                        const int64_t *q_rel, const float *g_rela_copies, const float *g_ar8_copies,
+                        const float *q_part, int32_t q_slices, float *g_rela, float *g_Wr, float *g_Wqr,
+                        float *g_bqr, float *g_w_alpha, float *g_b_alpha, void *stream);
 /* saved_plane_rows: rows per plane of `saved` (0 = n_nodes); lets a caller process only the first
  * n_nodes <= saved_plane_rows rows of buffers that were written with a larger row capacity. */
 int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_rows, const int64_t *n_nodes_dev,
@@ -281,7 +304,8 @@ int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_row
                     void *stream);
 
 /* Glue of the graph-captured training step (all shape-static, true counts read on the device):
- *   rg_gather_scores: backward of rg_scatter_scores, g_node[j] = g_scores_all[b_j][e_j] (0 past n);
+ *   rg_gather_scores: backward of rg_scatter_scores, g_node[j * out_stride] = g_scores_all[b_j][e_j] (0 past n);
+ *                     out_stride 8 writes whole rows {g, 0 x 7} = the g_small operand of rg_node_bwd;
  *   rg_scatter_rows : dst[src[j]] (+)= rows[j] for src[j] >= 0 -- gradient of the h0 re-index
  *                     (models.py:81), src = the inverse map of rg_frontier_remap;
  *   rg_query_sum8   : partial[q][32][0..23] = slice sums of rows24[.][0..23] over the node rows of query q
@@ -289,7 +313,7 @@ int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_row
  *                     per-query attention-bias gradient (cols 0..7) and the w_alpha / b_alpha sums. */
 int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
                      const int32_t *node_e, const float *g_scores_all, int32_t n_ent_out, float *g_node,
-                     void *stream);
+                     int32_t out_stride, void *stream);
 int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *src,
                     const float *rows, float *dst, int32_t accumulate, void *stream);
 int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *partial, void *stream);

@@ -60,15 +60,19 @@ SIGNATURES = {
     "rg_frontier_remap": (C.c_int, [C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 4),
-    "rg_node_update_train": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 9 + [C.c_int32] + [C.c_void_p] * 8),
-    "rg_node_bwd": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 7 + [C.c_int64] + [C.c_void_p] * 4
-                    + [C.c_int32, C.c_int32] + [C.c_void_p] * 5),
+    "rg_node_update_train": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 9 + [C.c_int32] + [C.c_void_p] * 4
+                             + [C.c_int32] + [C.c_void_p] * 4),
+    "rg_node_bwd": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 3 + [C.c_int32, C.c_void_p, C.c_int32]
+                    + [C.c_void_p] * 3 + [C.c_int64]
+                    + [C.c_void_p] * 4 + [C.c_int32, C.c_int32] + [C.c_void_p] * 5),
     "rg_node_wgrad_ctas": (C.c_int32, []),
     "rg_node_wgrad_out_floats": (C.c_int64, [C.c_int32]),
     "rg_node_wgrad": (C.c_int, [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 6
-                      + [C.c_int32] + [C.c_void_p] * 3),
+                      + [C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_void_p]),
+    "rg_attn_tables": (C.c_int, [C.c_int32] * 4 + [C.c_void_p] * 10),
+    "rg_attn_param_grads": (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 7 + [C.c_int32] + [C.c_void_p] * 7),
     "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64, C.c_int64] + [C.c_void_p] * 8),
-    "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),
+    "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "rg_scatter_rows": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
     "rg_query_sum8": (C.c_int, [C.c_int32] + [C.c_void_p] * 4),
     "rg_filtered_ranks": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 7),

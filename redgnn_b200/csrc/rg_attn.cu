@@ -1,0 +1,158 @@
+// Per-relation / per-query side of a GNN layer (reference Static/transductive/models.py:29-36):
+// the attention is factorised, so besides the per-edge kernels a layer needs two small tables
+//   ar8[r] = Wr_attn . rela[r]                     (one row per relation, 2R+1 rows)
+//   aq8[b] = Wqr_attn . rela[q_rel[b]] + b_qr      (one row per query)
+// and, in training, the parameter gradients that flow back through them.  Both are a few hundred rows
+// of D = 48: ONE kernel each instead of ~10 / ~25 framework launches per layer (which, at a few
+// microseconds apiece inside a captured step, had grown to a fifth of the FB15k-237 training step).
+#include "rg_common.cuh"
+
+namespace {
+
+// thread per output: ar8 [rows][8], aq8 [n][8], w8 [8]
+__global__ void __launch_bounds__(256) k_attn_tables(int D, int A, int rows, int n, const float *__restrict__ rela,
+                                                     const float *__restrict__ Wr, const float *__restrict__ Wqr,
+                                                     const float *__restrict__ bqr, const float *__restrict__ w_alpha,
+                                                     const int64_t *__restrict__ q_rel, float *__restrict__ ar8,
+                                                     float *__restrict__ aq8, float *__restrict__ w8) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int n_ar = rows * 8, n_aq = n * 8;
+    if (i < n_ar) {
+        const int r = i >> 3, k = i & 7;
+        float s = 0.f;
+        if (k < A)
+            for (int c = 0; c < D; ++c) s = fmaf(__ldg(rela + (size_t)r * D + c), __ldg(Wr + k * D + c), s);
+        ar8[i] = s;
+    } else if (i < n_ar + n_aq) {
+        const int j = i - n_ar, b = j >> 3, k = j & 7;
+        float s = 0.f;
+        if (k < A) {
+            const float *row = rela + (size_t)q_rel[b] * D;
+            s = __ldg(bqr + k);
+            for (int c = 0; c < D; ++c) s = fmaf(__ldg(row + c), __ldg(Wqr + k * D + c), s);
+        }
+        aq8[j] = s;
+    } else if (i < n_ar + n_aq + 8) {
+        const int k = i - n_ar - n_aq;
+        w8[k] = k < A ? __ldg(w_alpha + k) : 0.f;
+    }
+}
+
+// one CTA: every parameter gradient of a layer's attention / relation side, written in place
+constexpr int kPgThreads = 1024;
+__global__ void __launch_bounds__(kPgThreads) k_attn_param_grads(
+    int D, int A, int rows, int n, int copies, const float *__restrict__ rela, const float *__restrict__ Wr,
+    const float *__restrict__ Wqr, const int64_t *__restrict__ q_rel, const float *__restrict__ g_rela_c,
+    const float *__restrict__ g_ar8_c, const float *__restrict__ q_part, int q_slices, float *__restrict__ g_rela,
+    float *__restrict__ g_Wr, float *__restrict__ g_Wqr, float *__restrict__ g_bqr, float *__restrict__ g_w_alpha,
+    float *__restrict__ g_b_alpha) {
+    extern __shared__ float sm[];
+    float *s_gar = sm;                      // [rows][8]  sum over copies of g_ar8
+    float *s_gaq = s_gar + (size_t)rows * 8;  // [n][8]     per-query sums of g_as8 (= g_aq8)
+    float *s_w = s_gaq + (size_t)n * 8;       // [2][8][D]  Wr, Wqr (zero rows above A)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < rows * 8; i += kPgThreads) {
+        float s = 0.f;
+        for (int c = 0; c < copies; ++c) s += __ldg(g_ar8_c + (size_t)c * rows * 8 + i);
+        s_gar[i] = s;
+    }
+    for (int i = tid; i < n * 8; i += kPgThreads) {
+        const int b = i >> 3, k = i & 7;
+        float s = 0.f;
+        for (int sl = 0; sl < q_slices; ++sl) s += __ldg(q_part + ((size_t)b * q_slices + sl) * 24 + k);
+        s_gaq[i] = s;
+    }
+    for (int i = tid; i < 2 * 8 * D; i += kPgThreads) {
+        const int which = i / (8 * D), k = (i / D) & 7, c = i % D;
+        s_w[i] = k < A ? __ldg((which ? Wqr : Wr) + k * D + c) : 0.f;
+    }
+    // w_alpha.weight / bias: columns 8..8+A and 16 of the per-query partial sums, one warp per column
+    if (warp < 9) {
+        const int col = warp < 8 ? 8 + warp : 16;
+        float s = 0.f;
+        for (int i = lane; i < n * q_slices; i += 32) s += __ldg(q_part + (size_t)i * 24 + col);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(RG_FULL_MASK, s, o);
+        if (lane == 0) {
+            if (warp < 8) {
+                if (warp < A) g_w_alpha[warp] = s;
+            } else {
+                g_b_alpha[0] = s;
+            }
+        }
+    }
+    __syncthreads();
+    // Wr_attn.weight[k][c] = sum_r g_ar8[r][k] rela[r][c];  Wqr_attn.weight[k][c] = sum_b g_aq8[b][k] rela[q_rel[b]][c]
+    if (tid < A * D) {
+        const int k = tid / D, c = tid % D;
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s = fmaf(s_gar[r * 8 + k], __ldg(rela + (size_t)r * D + c), s);
+        g_Wr[tid] = s;
+    } else if (tid >= 512 && tid < 512 + A * D) {
+        const int j = tid - 512, k = j / D, c = j % D;
+        float s = 0.f;
+        for (int b = 0; b < n; ++b) s = fmaf(s_gaq[b * 8 + k], __ldg(rela + (size_t)q_rel[b] * D + c), s);
+        g_Wqr[j] = s;
+    }
+    if (tid >= kPgThreads - 32 && tid < kPgThreads - 32 + A) {   // Wqr_attn.bias[k] = sum_b g_aq8[b][k]
+        const int k = tid - (kPgThreads - 32);
+        float s = 0.f;
+        for (int b = 0; b < n; ++b) s += s_gaq[b * 8 + k];
+        g_bqr[k] = s;
+    }
+    // rela_embed.weight[r][c] = sum_copies g_rela + g_ar8[r] . Wr[:, c]   (+ the query part below)
+    for (int i = tid; i < rows * D; i += kPgThreads) {
+        const int r = i / D, c = i % D;
+        float s = 0.f;
+        for (int cp = 0; cp < copies; ++cp) s += __ldg(g_rela_c + (size_t)cp * rows * D + i);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s = fmaf(s_gar[r * 8 + k], s_w[k * D + c], s);
+        g_rela[i] = s;
+    }
+    __syncthreads();
+    // ... += g_aq8[b] . Wqr[:, c] into row q_rel[b]: queries in order by the same thread => deterministic
+    if (tid < D) {
+        for (int b = 0; b < n; ++b) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = fmaf(s_gaq[b * 8 + k], s_w[8 * D + k * D + tid], s);
+            g_rela[(size_t)q_rel[b] * D + tid] += s;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int rg_attn_tables(int32_t hidden_dim, int32_t attn_dim, int32_t n_rows, int32_t n_query, const float *rela,
+                              const float *Wr, const float *Wqr, const float *bqr, const float *w_alpha,
+                              const int64_t *q_rel, float *ar8, float *aq8, float *w8, void *stream) {
+    if (hidden_dim <= 0 || attn_dim < 1 || attn_dim > 8 || n_rows <= 0 || n_query <= 0) return RG_ERR_BAD_ARG;
+    if (!rela || !Wr || !Wqr || !bqr || !w_alpha || !q_rel || !ar8 || !aq8 || !w8) return RG_ERR_BAD_ARG;
+    const int total = (n_rows + n_query + 1) * 8;
+    k_attn_tables<<<(unsigned)rg_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(hidden_dim, attn_dim, n_rows, n_query,
+                                                                                 rela, Wr, Wqr, bqr, w_alpha, q_rel, ar8,
+                                                                                 aq8, w8);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}
+
+extern "C" int rg_attn_param_grads(int32_t hidden_dim, int32_t attn_dim, int32_t n_rows, int32_t n_query,
+                                   int32_t grad_copies, const float *rela, const float *Wr, const float *Wqr,
+                                   const int64_t *q_rel, const float *g_rela_copies, const float *g_ar8_copies,
+                                   const float *q_part, int32_t q_slices, float *g_rela, float *g_Wr, float *g_Wqr,
+                                   float *g_bqr, float *g_w_alpha, float *g_b_alpha, void *stream) {
+    if (hidden_dim <= 0 || hidden_dim > 64 || attn_dim < 1 || attn_dim > 8 || n_rows <= 0 || n_query <= 0 ||
+        grad_copies < 1 || q_slices < 1)
+        return RG_ERR_BAD_ARG;
+    if (!rela || !Wr || !Wqr || !q_rel || !g_rela_copies || !g_ar8_copies || !q_part || !g_rela || !g_Wr || !g_Wqr ||
+        !g_bqr || !g_w_alpha || !g_b_alpha)
+        return RG_ERR_BAD_ARG;
+    const size_t smem = ((size_t)n_rows * 8 + (size_t)n_query * 8 + 16 * hidden_dim) * sizeof(float);
+    if (smem > 200 * 1024) return RG_ERR_TOO_LARGE;
+    RG_CUDA_CALL(cudaFuncSetAttribute(k_attn_param_grads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_attn_param_grads<<<1, kPgThreads, smem, (cudaStream_t)stream>>>(
+        hidden_dim, attn_dim, n_rows, n_query, grad_copies, rela, Wr, Wqr, q_rel, g_rela_copies, g_ar8_copies, q_part,
+        q_slices, g_rela, g_Wr, g_Wqr, g_bqr, g_w_alpha, g_b_alpha);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}

@@ -256,11 +256,18 @@ __global__ void __launch_bounds__(256) k_gather_scores(int64_t n_host, const int
                                                        const int32_t *__restrict__ node_b,
                                                        const int32_t *__restrict__ node_e,
                                                        const float *__restrict__ g_all, int n_ent_out,
-                                                       float *__restrict__ g_node) {
+                                                       float *__restrict__ g_node, int stride) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n_host) return;
     const int64_t n = n_dev ? *n_dev : n_host;
-    g_node[i] = i < n ? g_all[(size_t)node_b[i] * n_ent_out + node_e[i]] : 0.f;
+    const float g = i < n ? g_all[(size_t)node_b[i] * n_ent_out + node_e[i]] : 0.f;
+    if (stride == 8) {   // row of a g_small [n][8] operand of rg_node_bwd: {g, 0 x 7}
+        float4 *o = reinterpret_cast<float4 *>(g_node + i * 8);
+        o[0] = make_float4(g, 0.f, 0.f, 0.f);
+        o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        g_node[i * stride] = g;
+    }
 }
 
 // dst[src[j]] = rows[j] for j < n with src[j] >= 0 (src injective): gradient of the h0 re-index
@@ -307,11 +314,12 @@ __global__ void __launch_bounds__(240) k_query_sum24(const float *__restrict__ r
 
 extern "C" int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
                                 const int32_t *node_e, const float *g_scores_all, int32_t n_ent_out, float *g_node,
-                                void *stream) {
-    if (n_nodes < 0 || !node_b || !node_e || !g_scores_all || !g_node || n_ent_out <= 0) return RG_ERR_BAD_ARG;
+                                int32_t out_stride, void *stream) {
+    if (n_nodes < 0 || !node_b || !node_e || !g_scores_all || !g_node || n_ent_out <= 0 || out_stride < 1)
+        return RG_ERR_BAD_ARG;
     if (n_nodes == 0) return RG_OK;
     k_gather_scores<<<(unsigned)rg_cdiv(n_nodes, 256), 256, 0, (cudaStream_t)stream>>>(
-        n_nodes, n_nodes_dev, node_b, node_e, g_scores_all, n_ent_out, g_node);
+        n_nodes, n_nodes_dev, node_b, node_e, g_scores_all, n_ent_out, g_node, out_stride);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -352,7 +360,7 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
                       const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                       const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                       const float *W_final, int32_t act, float *hidden, float *as8, float *score,
-                      const float *drop_mask, float *saved, cudaStream_t st);
+                      const float *drop_mask, float *saved, int32_t ws_rows, cudaStream_t st);
 
 // elementwise part of the GRU-cell backward (the GEMMs around it are plain library calls).
 // One CTA = kGruRows consecutive nodes x all D columns (thread = (row lane, column)); besides the
@@ -441,15 +449,16 @@ extern "C" int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const i
                                     const float *agg, const float *h_prev,
                                     const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
                                     const float *b_ih, const float *b_hh, int32_t act, const float *drop_mask,
-                                    float *hidden, float *saved, const float *Ws_next, const float *W_final,
-                                    float *as8, float *score, void *stream) {
+                                    float *hidden, float *saved, const float *Ws_next, int32_t ws_rows,
+                                    const float *W_final, float *as8, float *score, void *stream) {
     if (n_nodes < 0 || !agg || !W_h || !W_ih || !W_hh || !b_ih || !b_hh || !hidden || !saved) return RG_ERR_BAD_ARG;
     if ((h_prev == nullptr) != (src == nullptr) || act < 0 || act > 2) return RG_ERR_BAD_ARG;
     if ((as8 != nullptr) != (Ws_next != nullptr) || (score != nullptr) != (W_final != nullptr)) return RG_ERR_BAD_ARG;
+    if (Ws_next && (ws_rows < 1 || ws_rows > 8)) return RG_ERR_BAD_ARG;
     if (hidden_dim > 48) return RG_ERR_UNSUPPORTED;
     if (n_nodes == 0) return RG_OK;
     return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next,
-                             W_final, act, hidden, as8, score, drop_mask, saved, (cudaStream_t)stream);
+                             W_final, act, hidden, as8, score, drop_mask, saved, ws_rows, (cudaStream_t)stream);
 }
 
 extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *agg,
@@ -468,7 +477,7 @@ extern "C" int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t
     const char *force_simt = std::getenv("REDGNN_NODE_SIMT");
     if (hidden_dim <= 48 && !(force_simt && force_simt[0] == '1'))
         return rg_node_update_tc(hidden_dim, n_nodes, n_nodes_dev, agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh,
-                                 Ws_next, W_final, act, hidden, as8, score, nullptr, nullptr, st);
+                                 Ws_next, W_final, act, hidden, as8, score, nullptr, nullptr, 8, st);
 #define RG_NODE(DD)                                                                                              \
     return h_prev ? launch_node<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,   \
                                           n_nodes, n_nodes_dev, hidden, as8, score, st)                                       \

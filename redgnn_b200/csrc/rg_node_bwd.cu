@@ -116,8 +116,9 @@ __device__ __forceinline__ void issue_gemm_ts(uint32_t smem_base, uint32_t tmem_
 
 template <int D, bool HAS_H0>
 __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
-    const float *__restrict__ g_hidden, const float *__restrict__ g_small, const float *__restrict__ w_small,
-    const float *__restrict__ g_h0_next, const int32_t *__restrict__ remap, const float *__restrict__ saved,
+    const float *__restrict__ g_hidden, const float *__restrict__ g_small, int g_small_stride,
+    const float *__restrict__ w_small, int w_small_rows, const float *__restrict__ g_h0_next, const int32_t *__restrict__ remap,
+    const float *__restrict__ saved,
     int64_t plane_rows, const float *__restrict__ drop_mask, const float *__restrict__ W_h,
     const float *__restrict__ W_ih, const float *__restrict__ W_hh, int act, int64_t n_nodes_host,
     const int64_t *__restrict__ n_nodes_dev, float *__restrict__ G4, float *__restrict__ g_pre_out,
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
             *reinterpret_cast<float *>(smem + L::W_LO + o) = v[e] - hi;
         }
     }
-    for (int i = tid; i < 8 * D; i += kThreads) wsm[i] = w_small ? w_small[i] : 0.f;
+    for (int i = tid; i < 8 * D; i += kThreads) wsm[i] = (w_small && i < w_small_rows * D) ? w_small[i] : 0.f;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -194,8 +195,8 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
             if (live) {
                 if (g_hidden) ld16(g_hidden + o, g);
                 if (g_small) {
-                    const float4 s0 = __ldg(reinterpret_cast<const float4 *>(g_small + (size_t)row * 8));
-                    const float4 s1 = __ldg(reinterpret_cast<const float4 *>(g_small + (size_t)row * 8) + 1);
+                    const float4 s0 = __ldg(reinterpret_cast<const float4 *>(g_small + (size_t)row * g_small_stride));
+                    const float4 s1 = __ldg(reinterpret_cast<const float4 *>(g_small + (size_t)row * g_small_stride) + 1);
                     const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
                     for (int a = 0; a < 8; ++a)
@@ -316,7 +317,8 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_bwd_tc(
 }
 
 template <int D, bool HH>
-int launch_node_bwd(const float *g_hidden, const float *g_small, const float *w_small, const float *g_h0_next,
+int launch_node_bwd(const float *g_hidden, const float *g_small, int g_small_stride, const float *w_small,
+                    int w_small_rows, const float *g_h0_next,
                     const int32_t *remap, const float *saved, int64_t plane_rows, const float *drop_mask,
                     const float *W_h, const float *W_ih, const float *W_hh, int act, int64_t n_nodes,
                     const int64_t *n_nodes_dev, float *G4, float *g_pre, float *g_agg, float *g_h0, cudaStream_t st) {
@@ -329,7 +331,9 @@ int launch_node_bwd(const float *g_hidden, const float *g_small, const float *w_
     RG_CUDA_CALL(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     const int64_t n_tiles = (n_nodes + kTcRows - 1) / kTcRows;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);  // persistent: one CTA per SM (it owns all of TMEM)
-    kern<<<grid, 128 * (D / 16), smem, st>>>(g_hidden, g_small, w_small, g_h0_next, remap, saved, plane_rows, drop_mask,
+    kern<<<grid, 128 * (D / 16), smem, st>>>(g_hidden, g_small, g_small_stride, w_small, w_small_rows, g_h0_next, remap, saved,
+                                             plane_rows,
+                                             drop_mask,
                                              W_h, W_ih, W_hh, act, n_nodes, n_nodes_dev, G4, g_pre, g_agg, g_h0);
     RG_LAUNCH_CHECK();
     return RG_OK;
@@ -364,7 +368,7 @@ struct Wg {
     // output layout
     static constexpr int O_WIH = 0, O_WHH = 3 * D * D, O_WH = 6 * D * D, O_WS = 7 * D * D, O_B = 7 * D * D + 8 * D;
     static constexpr int OUT = O_B + 4 * D;
-    static WgLayout layout(bool has_mask, bool has_h0, bool has_small) {
+    static WgLayout layout(bool has_mask, bool has_h0, bool has_small, int small_stride) {
         WgLayout l;
         constexpr int IL = il_tile_floats(D);       // one lane-interleaved tile (padded chunks)
         int o = 0;
@@ -375,7 +379,7 @@ struct Wg {
         l.ohid = has_small ? o : -1, o += has_small ? KS * D : 0;
         l.og4 = o, o += 4 * IL;
         l.ogp = o, o += IL;
-        l.ogs = has_small ? o : -1, o += has_small ? KS * 8 : 0;
+        l.ogs = has_small ? o : -1, o += has_small ? KS * small_stride : 0;
         l.stage = o;
         return l;
     }
@@ -395,7 +399,7 @@ template <int D, bool HAS_H0>
 __global__ void __maxnreg__(112) k_node_wgrad(
     const float *__restrict__ saved, int64_t plane_rows, const float *__restrict__ drop_mask,
     const float *__restrict__ agg, const float *__restrict__ hidden, const float *__restrict__ G4,
-    const float *__restrict__ g_pre, const float *__restrict__ g_small, int64_t n_nodes_host,
+    const float *__restrict__ g_pre, const float *__restrict__ g_small, int g_small_stride, int64_t n_nodes_host,
     const int64_t *__restrict__ n_nodes_dev, float *__restrict__ partial, WgLayout L) {
     using W = Wg<D>;
     extern __shared__ __align__(128) float wg_smem[];
@@ -428,7 +432,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
             out = W::O_WH + 8 * (t / IB) * D + 8 * (t % IB), kind = 0;
         } else if ((t -= W::T3) < W::T4) {
             xo = L.ohid + 8 * t, xk = D, xh = 4;                               // hidden, g_small: row-major
-            go = L.ogs, gk = 8, gh = 4, out = W::O_WS + 8 * t, kind = has_small ? 0 : 2;
+            go = L.ogs, gk = g_small_stride, gh = 4, out = W::O_WS + 8 * t, kind = has_small ? 0 : 2;
         } else if ((t -= W::T4) < W::T5) {
             go = g4(8 * t), out = W::O_B + 8 * t, kind = 1;
         }
@@ -452,7 +456,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
         uint32_t total = tb * 6 + rb;                                     // x_act, 4 x G4, g_pre; agg
         if (has_mask) total += rb;
         if (HAS_H0) total += tb;
-        if (has_small) total += rb + rows * 32;
+        if (has_small) total += rb + rows * g_small_stride * 4;
         mbar_expect_tx(full + s, total);
         const size_t toff = (size_t)(base >> 5) * il_tile_floats(D);   // this tile inside an interleaved plane
         bulk_g2s(st + L.ox, saved + toff, tb, full + s);
@@ -465,7 +469,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
         bulk_g2s(st + L.ogp, g_pre + toff, tb, full + s);
         if (has_small) {
             bulk_g2s(st + L.ohid, hidden + (size_t)base * D, rb, full + s);
-            bulk_g2s(st + L.ogs, g_small + (size_t)base * 8, rows * 32, full + s);
+            bulk_g2s(st + L.ogs, g_small + (size_t)base * g_small_stride, rows * g_small_stride * 4, full + s);
         }
     };
     if (tid == 0)
@@ -545,12 +549,21 @@ __global__ void __maxnreg__(112) k_node_wgrad(
     }
 }
 
-// out[o] = sum over CTAs of partial[cta][o] in a FIXED order (8 interleaved groups of CTAs, each summed
-// ascending, then a fixed tree over the groups): deterministic, and 8x shorter dependent chains than
-// one thread per output.  Outputs of idle tiles (no h0 / no g_small) are zero.
+// sum over CTAs of partial[cta][o] in a FIXED order (8 interleaved groups of CTAs, each summed ascending,
+// then a fixed tree over the groups): deterministic, and 8x shorter dependent chains than one thread per
+// output.  The sums go straight to their destinations: either the packed `out` vector (rg_node_wgrad), or
+// the parameter gradients themselves (rg_node_wgrad_into: the GRU weights / biases ACCUMULATE over the
+// layers, W_h / the small projection are per layer).  Outputs of idle tiles (no h0 / no g_small) are zero.
+struct WgDst {
+    float *out;                                   // packed [OUT] or NULL
+    float *wih, *whh, *bih, *bhh;                 // += (GRU parameters, shared by all layers)
+    float *wh, *ws;                               // =  (W_h [D][D]; small projection, first ws_rows rows of [8][D])
+    int ws_rows;
+};
+
 template <int D, bool HAS_H0>
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float *__restrict__ partial, int n_ctas, int has_small,
-                                                      float *__restrict__ out) {
+                                                      WgDst dst) {
     using W = Wg<D>;
     __shared__ float sm[8][32];
     const int ol = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -571,25 +584,44 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float *__restrict__ 
     }
     sm[grp][ol] = s;
     __syncthreads();
-    if (grp == 0 && o < W::OUT)
-        out[o] = ((sm[0][ol] + sm[1][ol]) + (sm[2][ol] + sm[3][ol])) + ((sm[4][ol] + sm[5][ol]) + (sm[6][ol] + sm[7][ol]));
+    if (grp != 0 || o >= W::OUT) return;
+    const float v = ((sm[0][ol] + sm[1][ol]) + (sm[2][ol] + sm[3][ol])) + ((sm[4][ol] + sm[5][ol]) + (sm[6][ol] + sm[7][ol]));
+    if (dst.out) {
+        dst.out[o] = v;
+        return;
+    }
+    if (o < W::O_WHH) {
+        dst.wih[o] += v;
+    } else if (o < W::O_WH) {
+        dst.whh[o - W::O_WHH] += v;
+    } else if (o < W::O_WS) {
+        dst.wh[o - W::O_WH] = v;
+    } else if (o < W::O_B) {
+        const int j = o - W::O_WS;
+        if (dst.ws && j < dst.ws_rows * D) dst.ws[j] = v;
+    } else {                                      // column sums of g_r', g_z', g_n', g_n' r
+        const int j = o - W::O_B, g = j / D, c = j % D;
+        if (g < 3) dst.bih[j] += v;               // b_ih: r, z, n
+        if (g < 2) dst.bhh[j] += v;               // b_hh: r, z, (n from g_n' r)
+        if (g == 3) dst.bhh[2 * D + c] += v;
+    }
 }
 
 template <int D, bool HH>
 int launch_wgrad(const float *saved, int64_t plane_rows, const float *drop_mask, const float *agg, const float *hidden,
-                 const float *G4, const float *g_pre, const float *g_small, int64_t n_nodes, const int64_t *n_nodes_dev,
-                 float *partial, float *out, cudaStream_t st) {
+                 const float *G4, const float *g_pre, const float *g_small, int g_small_stride, int64_t n_nodes,
+                 const int64_t *n_nodes_dev, float *partial, WgDst dst, cudaStream_t st) {
     using W = Wg<D>;
-    const WgLayout L = W::layout(drop_mask != nullptr, HH, g_small != nullptr);
+    const WgLayout L = W::layout(drop_mask != nullptr, HH, g_small != nullptr, g_small_stride);
     const size_t smem = (size_t)kWgStages * L.stage * 4 + 64;   // + mbarriers
     auto kern = k_node_wgrad<D, HH>;
     RG_CUDA_CALL(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t n_slabs = rg_cdiv(n_nodes, kWgNodes);
     const int grid = (int)(n_slabs < kWgCtas ? n_slabs : kWgCtas);
-    kern<<<grid, W::THREADS, smem, st>>>(saved, plane_rows, drop_mask, agg, hidden, G4, g_pre, g_small, n_nodes, n_nodes_dev,
-                                        partial, L);
+    kern<<<grid, W::THREADS, smem, st>>>(saved, plane_rows, drop_mask, agg, hidden, G4, g_pre, g_small, g_small_stride,
+                                        n_nodes, n_nodes_dev, partial, L);
     RG_LAUNCH_CHECK();
-    k_wgrad_reduce<D, HH><<<(W::OUT + 31) / 32, 256, 0, st>>>(partial, grid, g_small != nullptr, out);
+    k_wgrad_reduce<D, HH><<<(W::OUT + 31) / 32, 256, 0, st>>>(partial, grid, g_small != nullptr, dst);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -597,24 +629,28 @@ int launch_wgrad(const float *saved, int64_t plane_rows, const float *drop_mask,
 }  // namespace
 
 extern "C" int rg_node_bwd(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *g_hidden,
-                           const float *g_small, const float *w_small, const float *g_h0_next, const int32_t *remap,
-                           const float *saved, int64_t saved_plane_rows, const float *drop_mask, const float *W_h,
-                           const float *W_ih, const float *W_hh, int32_t act, int32_t has_h0, float *G4, float *g_pre,
-                           float *g_agg, float *g_h0, void *stream) {
+                           const float *g_small, int32_t g_small_stride, const float *w_small, int32_t w_small_rows,
+                           const float *g_h0_next,
+                           const int32_t *remap, const float *saved, int64_t saved_plane_rows, const float *drop_mask,
+                           const float *W_h, const float *W_ih, const float *W_hh, int32_t act, int32_t has_h0, float *G4,
+                           float *g_pre, float *g_agg, float *g_h0, void *stream) {
     if (n_nodes < 0 || !saved || !W_h || !W_ih || !W_hh || !G4 || !g_pre || !g_agg || act < 0 || act > 2)
         return RG_ERR_BAD_ARG;
     if (!g_hidden && !g_small && !g_h0_next) return RG_ERR_BAD_ARG;
     if ((g_small == nullptr) != (w_small == nullptr) || (g_h0_next == nullptr) != (remap == nullptr)) return RG_ERR_BAD_ARG;
+    if (g_small && (g_small_stride < 8 || g_small_stride % 4 || w_small_rows < 1 || w_small_rows > 8)) return RG_ERR_BAD_ARG;
     if (has_h0 && !g_h0) return RG_ERR_BAD_ARG;
     if (n_nodes == 0) return RG_OK;
     const int64_t plane = saved_plane_rows > 0 ? saved_plane_rows : n_nodes;
     if (plane < n_nodes) return RG_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-#define RG_NB(DD)                                                                                                     \
-    return has_h0 ? launch_node_bwd<DD, true>(g_hidden, g_small, w_small, g_h0_next, remap, saved, plane, drop_mask,   \
-                                              W_h, W_ih, W_hh, act, n_nodes, n_nodes_dev, G4, g_pre, g_agg, g_h0, st)  \
-                  : launch_node_bwd<DD, false>(g_hidden, g_small, w_small, g_h0_next, remap, saved, plane, drop_mask,  \
-                                               W_h, W_ih, W_hh, act, n_nodes, n_nodes_dev, G4, g_pre, g_agg, g_h0, st)
+#define RG_NB(DD)                                                                                                      \
+    return has_h0 ? launch_node_bwd<DD, true>(g_hidden, g_small, g_small_stride, w_small, w_small_rows, g_h0_next, remap, saved, plane, \
+                                              drop_mask, W_h, W_ih, W_hh, act, n_nodes, n_nodes_dev, G4, g_pre, g_agg,  \
+                                              g_h0, st)                                                                \
+                  : launch_node_bwd<DD, false>(g_hidden, g_small, g_small_stride, w_small, w_small_rows, g_h0_next, remap, saved,     \
+                                               plane, drop_mask, W_h, W_ih, W_hh, act, n_nodes, n_nodes_dev, G4, g_pre, \
+                                               g_agg, g_h0, st)
     switch (hidden_dim) {
         case 16: RG_NB(16);
         case 32: RG_NB(32);
@@ -637,18 +673,22 @@ extern "C" int64_t rg_node_wgrad_out_floats(int32_t hidden_dim) {
 
 extern "C" int rg_node_wgrad(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const float *saved,
                              int64_t saved_plane_rows, const float *drop_mask, const float *agg, const float *hidden,
-                             const float *G4, const float *g_pre, const float *g_small, int32_t has_h0, float *partial,
-                             float *out, void *stream) {
-    if (n_nodes <= 0 || !saved || !agg || !G4 || !g_pre || !partial || !out) return RG_ERR_BAD_ARG;
-    if (g_small && !hidden) return RG_ERR_BAD_ARG;
+                             const float *G4, const float *g_pre, const float *g_small, int32_t g_small_stride,
+                             int32_t has_h0, float *partial, float *out, float *g_wih, float *g_whh, float *g_bih,
+                             float *g_bhh, float *g_wh, float *g_ws, int32_t ws_rows, void *stream) {
+    if (n_nodes <= 0 || !saved || !agg || !G4 || !g_pre || !partial) return RG_ERR_BAD_ARG;
+    if (!out && (!g_wih || !g_whh || !g_bih || !g_bhh || !g_wh)) return RG_ERR_BAD_ARG;
+    if (g_small && (!hidden || g_small_stride < 8 || g_small_stride % 4)) return RG_ERR_BAD_ARG;
+    if (ws_rows < 0 || ws_rows > 8) return RG_ERR_BAD_ARG;
     const int64_t plane = saved_plane_rows > 0 ? saved_plane_rows : n_nodes;
     if (plane < n_nodes) return RG_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
+    WgDst dst = {out, g_wih, g_whh, g_bih, g_bhh, g_wh, g_ws, ws_rows};
 #define RG_WG(DD)                                                                                                    \
-    return has_h0 ? launch_wgrad<DD, true>(saved, plane, drop_mask, agg, hidden, G4, g_pre, g_small, n_nodes,         \
-                                           n_nodes_dev, partial, out, st)                                            \
-                  : launch_wgrad<DD, false>(saved, plane, drop_mask, agg, hidden, G4, g_pre, g_small, n_nodes,        \
-                                            n_nodes_dev, partial, out, st)
+    return has_h0 ? launch_wgrad<DD, true>(saved, plane, drop_mask, agg, hidden, G4, g_pre, g_small, g_small_stride,  \
+                                           n_nodes, n_nodes_dev, partial, dst, st)                                   \
+                  : launch_wgrad<DD, false>(saved, plane, drop_mask, agg, hidden, G4, g_pre, g_small, g_small_stride, \
+                                            n_nodes, n_nodes_dev, partial, dst, st)
     switch (hidden_dim) {
         case 16: RG_WG(16);
         case 32: RG_WG(32);

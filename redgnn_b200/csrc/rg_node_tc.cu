@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
     const float *__restrict__ b_ih, const float *__restrict__ b_hh, const float *__restrict__ Ws_next,
     const float *__restrict__ W_final, int act, int64_t n_nodes_host, const int64_t *__restrict__ n_nodes_dev,
     float *__restrict__ hidden, float *__restrict__ as8, float *__restrict__ score,
-    const float *__restrict__ drop_mask, float *__restrict__ saved) {
+    const float *__restrict__ drop_mask, float *__restrict__ saved, int ws_rows) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using L = TcSmem<D>;
     constexpr int KC = L::KC;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(128 * (D / 16), 1) k_node_update_tc(
     for (int i = tid; i < 9 * D; i += kTcThreads) {
         float v = 0.f;
         if (i < 8 * D) {
-            if (Ws_next) v = Ws_next[i];
+            if (Ws_next && i < ws_rows * D) v = Ws_next[i];   // rows >= ws_rows (attn_dim) are zero
         } else if (W_final) {
             v = W_final[i - 8 * D];
         }
@@ -346,7 +346,7 @@ template <int D, bool HH>
 int launch_node_tc(const float *agg, const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                    const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                    const float *W_final, int act, int64_t n_nodes, const int64_t *n_nodes_dev, float *hidden,
-                   float *as8, float *score, const float *drop_mask, float *saved, cudaStream_t st) {
+                   float *as8, float *score, const float *drop_mask, float *saved, int ws_rows, cudaStream_t st) {
     constexpr size_t smem = TcSmem<D>::TOTAL;
     static_assert(smem <= 232448, "tile does not fit the 227 KB shared memory of one CTA");
     auto kern = k_node_update_tc<D, HH>;
@@ -357,7 +357,7 @@ int launch_node_tc(const float *agg, const float *h_prev, const int32_t *src, co
     const int64_t n_tiles = (n_nodes + kTcRows - 1) / kTcRows;
     const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);  // persistent: one CTA per SM
     kern<<<grid, 128 * (D / 16), smem, st>>>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,
-                                         n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved);
+                                         n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, ws_rows);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -370,12 +370,12 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
                       const float *h_prev, const int32_t *src, const float *W_h, const float *W_ih,
                       const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                       const float *W_final, int32_t act, float *hidden, float *as8, float *score,
-                      const float *drop_mask, float *saved, cudaStream_t st) {
+                      const float *drop_mask, float *saved, int32_t ws_rows, cudaStream_t st) {
 #define RG_NODE_TC(DD)                                                                                             \
     return h_prev ? launch_node_tc<DD, true>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act,  \
-                                             n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, st)       \
+                                             n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, ws_rows, st)       \
                   : launch_node_tc<DD, false>(agg, h_prev, src, W_h, W_ih, W_hh, b_ih, b_hh, Ws_next, W_final, act, \
-                                              n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, st)
+                                              n_nodes, n_nodes_dev, hidden, as8, score, drop_mask, saved, ws_rows, st)
     switch (hidden_dim) {
         case 16: RG_NODE_TC(16);
         case 32: RG_NODE_TC(32);

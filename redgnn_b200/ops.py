@@ -196,7 +196,7 @@ class NodeUpdateTrain(torch.autograd.Function):
         with _lib.Stats.timed("node_update_train", (n, d)):
             check(lib.rg_node_update_train(d, n, None, ptr(agg), ptr(h_prev), ptr(src), ptr(W_h), ptr(w_ih), ptr(w_hh),
                                            ptr(b_ih), ptr(b_hh), act_code, ptr(mask), ptr(hidden), ptr(saved),
-                                           None, None, None, None, stream_ptr()))
+                                           None, 0, None, None, None, stream_ptr()))
         _lib.Stats.launches += 1
         ctx.save_for_backward(agg, saved, W_h, w_ih, w_hh, mask if mask is not None else agg.new_empty(0),
                               remap if remap is not None else agg.new_empty(0, dtype=torch.int64))
@@ -215,14 +215,15 @@ class NodeUpdateTrain(torch.autograd.Function):
         g_h0 = e(n, d) if ctx.has_h0 else None
         mk = mask if ctx.has_mask else None
         with _lib.Stats.timed("node_bwd", (n, d)):
-            check(lib.rg_node_bwd(d, n, None, ptr(g_h), None, None, None, None, ptr(saved), n, ptr(mk), ptr(W_h),
+            check(lib.rg_node_bwd(d, n, None, ptr(g_h), None, 8, None, 0, None, None, ptr(saved), n, ptr(mk), ptr(W_h),
                                   ptr(w_ih), ptr(w_hh), ctx.act_code, int(ctx.has_h0), ptr(G4), ptr(g_pre), ptr(g_agg),
                                   ptr(g_h0), stream_ptr()))
         out_floats = int(lib.rg_node_wgrad_out_floats(d))
         partial, wg = e(int(lib.rg_node_wgrad_ctas()) * out_floats), e(out_floats)
         with _lib.Stats.timed("node_wgrad", (n, d)):
-            check(lib.rg_node_wgrad(d, n, None, ptr(saved), n, ptr(mk), ptr(agg), None, ptr(G4), ptr(g_pre), None,
-                                    int(ctx.has_h0), ptr(partial), ptr(wg), stream_ptr()))
+            check(lib.rg_node_wgrad(d, n, None, ptr(saved), n, ptr(mk), ptr(agg), None, ptr(G4), ptr(g_pre), None, 8,
+                                    int(ctx.has_h0), ptr(partial), ptr(wg), None, None, None, None, None, None, 0,
+                                    stream_ptr()))
         _lib.Stats.launches += 3
         o_whh, o_wh, o_ws, o_b = 3 * d * d, 6 * d * d, 7 * d * d, 7 * d * d + 8 * d
         d_wih, d_whh, d_wh = wg[:o_whh].view(3 * d, d), wg[o_whh:o_wh].view(3 * d, d), wg[o_wh:o_ws].view(d, d)

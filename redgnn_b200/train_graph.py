@@ -32,10 +32,6 @@ from ._lib import lib, check, ptr, stream_ptr
 from .ops import Segments, _Heavy, ACT_CODES
 
 
-def _pad_rows(w, rows=8):
-    return w if w.shape[0] == rows else F.pad(w, (0, 0, 0, rows - w.shape[0]))
-
-
 class TrainStepRunner(object):
     """Static buffers + the two CUDA graphs for one (model, KG, batch size)."""
 
@@ -66,6 +62,10 @@ class TrainStepRunner(object):
         self.plane = _lib.il_plane_floats(self.cap, self.d)
         self.saved = [z(6, self.plane) for _ in range(self.n_layer)]
         self.as8 = [z(self.cap, 8) for _ in range(self.n_layer - 1)]       # next layer's Ws_attn(hidden), per node
+        rows = 2 * model.n_rel + 1                                         # attention tables (rg_attn_tables)
+        self.ar8 = [z(rows, 8) for _ in range(self.n_layer)]
+        self.aq8 = [z(self.n, 8) for _ in range(self.n_layer)]
+        self.w8 = [z(8) for _ in range(self.n_layer)]
         self.score_node = z(self.cap)
         self.wg_out_floats = int(lib.rg_node_wgrad_out_floats(self.d))
         self.wg_partial = torch.empty(int(lib.rg_node_wgrad_ctas()) * self.wg_out_floats, dtype=torch.float32, device=dev)
@@ -80,7 +80,7 @@ class TrainStepRunner(object):
 
     # ------------------------------------------------------------------------------------------
     def _forward(self):
-        m, g, n, d, cap, dev = self.model, self.graph, self.n, self.d, self.cap, self.dev
+        m, g, n, d, a, cap, dev = self.model, self.graph, self.n, self.d, self.a, self.cap, self.dev
         q_sub, q_rel = self.sub, self.rel
         batch = torch.arange(n, device=dev)
         fr = g.frontier_from_nodes(torch.stack([batch, q_sub], dim=1), n)
@@ -88,9 +88,8 @@ class TrainStepRunner(object):
         # (an out-of-range subject is dropped by the frontier kernels and flagged in RG_CNT_ERR; clamped here so
         # that the layer-0 backward segments, which index the CSR by it, stay in bounds)
         node_b, node_e = batch.to(torch.int32), q_sub.clamp(0, g.n_ent - 1).to(torch.int32)
-        onehot = torch.zeros((n, 2 * m.n_rel + 1), dtype=torch.float32, device=dev)
-        onehot.scatter_(1, q_rel[:, None], 1.0)
         hidden, n_in_dev, L = None, None, []
+        gate = m.gate
         for i in range(self.n_layer):
             layer = m.gnn_layers[i]
             fr_next = g.step(fr)
@@ -100,13 +99,10 @@ class TrainStepRunner(object):
             # forward; remap: old_nodes_new_idx as int32 for the g_h0 gather of the backward (layers >= 1)
             remap, src = fr.remaps32(fr_next, cap, cap) if hidden is not None else (None, None)
             rela = layer.rela_embed.weight
-            Ws8, Wr8, Wqr8 = _pad_rows(layer.Ws_attn.weight), _pad_rows(layer.Wr_attn.weight), \
-                _pad_rows(layer.Wqr_attn.weight)
-            bqr8 = F.pad(layer.Wqr_attn.bias, (0, 8 - self.a))
-            w8 = F.pad(layer.w_alpha.weight.reshape(-1), (0, 8 - self.a)).contiguous()
-            ar8 = (rela @ Wr8.t()).contiguous()
-            hq = onehot @ rela                                   # rela[q_rel], as a GEMM (deterministic backward)
-            aq8 = torch.addmm(bqr8, hq, Wqr8.t()).contiguous()
+            ar8, aq8, w8 = self.ar8[i], self.aq8[i], self.w8[i]
+            check(lib.rg_attn_tables(d, a, rela.shape[0], n, ptr(rela), ptr(layer.Wr_attn.weight),
+                                     ptr(layer.Wqr_attn.weight), ptr(layer.Wqr_attn.bias), ptr(layer.w_alpha.weight),
+                                     ptr(q_rel), ptr(ar8), ptr(aq8), ptr(w8), stream_ptr()))
             as8 = self.as8[i - 1] if hidden is not None else None   # written by the previous node update
             fwd_seg = Segments.implicit(nb, ne, g.in_ptr, g.in_adj, fr, g.heavy_in)
             fwd_seg.n_seg_dev, fwd_seg.n_table_rows = n_dev, rela.shape[0]
@@ -117,127 +113,108 @@ class TrainStepRunner(object):
             check(lib.rg_edge_agg_fwd(C.byref(fwd_seg.c_struct()), d, ptr(hidden), ptr(as8), ptr(rela), ptr(ar8),
                                       ptr(aq8), ptr(w8), ptr(layer.w_alpha.bias), ptr(self.agg[i]), heavy.ref(),
                                       stream_ptr()))
-            _lib.Stats.launches += (3 if heavy.struct is not None else 1) + 1      # + node update below
+            _lib.Stats.launches += (2 if heavy.struct is not None else 1) + 2      # + tables, node update
             mask = None
             if self.p_drop > 0:
                 keep = 1.0 - self.p_drop
                 mask = (torch.rand((cap, d), device=dev) < keep).to(torch.float32).div_(keep)
-            gate = m.gate
             last = i == self.n_layer - 1
             # the node kernel also emits the NEXT layer's attention projection Ws_attn(hidden) / the scores
-            ws_next = None if last else _pad_rows(m.gnn_layers[i + 1].Ws_attn.weight).contiguous()
+            ws_next = None if last else m.gnn_layers[i + 1].Ws_attn.weight
             check(lib.rg_node_update_train(d, cap, ptr(n_dev), ptr(self.agg[i]), ptr(hidden), ptr(src),
                                            ptr(layer.W_h.weight), ptr(gate.weight_ih_l0), ptr(gate.weight_hh_l0),
                                            ptr(gate.bias_ih_l0), ptr(gate.bias_hh_l0), self.act_code, ptr(mask),
-                                           ptr(self.hidden[i]), ptr(self.saved[i]), ptr(ws_next),
+                                           ptr(self.hidden[i]), ptr(self.saved[i]), ptr(ws_next), a,
                                            ptr(m.W_final.weight) if last else None,
                                            ptr(self.as8[i]) if not last else None,
                                            ptr(self.score_node) if last else None, stream_ptr()))
-            L.append(dict(fr_in=fr, fr_out=fr_next, n_dev=n_dev, nb=nb, ne=ne, src=src, remap=remap, ws_next=ws_next,
-                          rela=rela, Ws8=Ws8, Wr8=Wr8,
-                          Wqr8=Wqr8, w8=w8, ar8=ar8, hq=hq, aq8=aq8, as8=as8, hidden_prev=hidden, mask=mask,
-                          bwd_seg=bwd_seg, heavy=heavy, fwd_seg=fwd_seg))
+            L.append(dict(fr_in=fr, fr_out=fr_next, n_dev=n_dev, nb=nb, ne=ne, src=src, remap=remap, rela=rela,
+                          w8=w8, ar8=ar8, aq8=aq8, as8=as8, hidden_prev=hidden, mask=mask, bwd_seg=bwd_seg,
+                          heavy=heavy, fwd_seg=fwd_seg))
             hidden, n_in_dev, fr, node_b, node_e = self.hidden[i], n_dev, fr_next, nb, ne
         scores = torch.zeros((n, self.n_ent_out), dtype=torch.float32, device=dev)
         check(lib.rg_scatter_scores(cap, ptr(n_in_dev), ptr(node_b), ptr(node_e), ptr(self.score_node), self.n_ent_out,
                                     ptr(scores), stream_ptr()))
         _lib.Stats.launches += 1
-        self.L, self.onehot = L, onehot
+        self.L = L
         return scores
 
     # ------------------------------------------------------------------------------------------
     def _backward(self, caps=None):
         """Hand-written backward of the whole path on the buffers of the last forward replay.  Every
         kernel stops at the device-side node counts, so nothing here depends on the true sizes
-        (`caps` is accepted for compatibility and ignored): ONE captured variant, no host read-back.
+        (`caps` is accepted for compatibility and ignored): ONE captured variant, no host read-back,
+        and every parameter gradient is written (or accumulated) IN PLACE in the flat gradient buffer.
         Per layer, last to first:  rg_node_bwd (tensor cores: GRU / W_h data gradients, with the next
         layer's attention-projection and GRU-state paths folded in as gathers)  ->  rg_node_wgrad
-        (weight gradients)  ->  rg_edge_agg_bwd (fused edge backward)  ->  per-relation / per-query
-        projections (tiny, torch)."""
+        (weight gradients)  ->  rg_edge_agg_bwd (fused edge backward)  ->  rg_query_sum8 +
+        rg_attn_param_grads (per-relation / per-query parameter gradients)."""
         m, n, d, a, dev, cap = self.model, self.n, self.d, self.a, self.dev, self.cap
         st = stream_ptr
         z = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
         e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-        grads = {}
+        gv = self.grad_views
+        self.flat_grad.zero_()                                   # the GRU gradients accumulate over the layers
         last = self.L[-1]
-        # upstream of the last layer: g_hidden = g_score * W_final, expressed as g_small . w_small
-        g_node = e(cap)
+        # upstream of the last layer: g_hidden = g_score * W_final, expressed as g_small . w_small (1 row)
+        g_small = e(cap, 8)
         check(lib.rg_gather_scores(cap, ptr(last["n_dev"]), ptr(last["nb"]), ptr(last["ne"]), ptr(self.g_out),
-                                   self.n_ent_out, ptr(g_node), st()))
+                                   self.n_ent_out, ptr(g_small), 8, st()))
         _lib.Stats.launches += 1
-        g_small = z(cap, 8)
-        g_small[:, 0] = g_node
-        w_small = F.pad(m.W_final.weight, (0, 0, 0, 7)).contiguous()          # [8, d], row 0 = W_final
+        g_small_stride, w_small, w_rows, ws_dst = 8, m.W_final.weight, 1, gv["W_final.weight"]
         g_hid_e, g_h0_next, remap = None, None, None
         gate = m.gate
         w_ih, w_hh = gate.weight_ih_l0, gate.weight_hh_l0
-        d_wih, d_whh, d_bih, d_bhh = torch.zeros_like(w_ih), torch.zeros_like(w_hh), z(3 * d), z(3 * d)
-        O_WHH, O_WH, O_WS, O_B = 3 * d * d, 6 * d * d, 7 * d * d, 7 * d * d + 8 * d
+        copies = _lib.GRAD_COPIES
         for i in reversed(range(self.n_layer)):
             lay, layer = self.L[i], m.gnn_layers[i]
             pre = "gnn_layers.%d." % i
             has_h0 = lay["hidden_prev"] is not None
             G4, g_pre, g_agg = e(4, self.plane), e(self.plane), e(cap, d)
             g_h0 = e(cap, d) if has_h0 else None
-            check(lib.rg_node_bwd(d, cap, ptr(lay["n_dev"]), ptr(g_hid_e), ptr(g_small), ptr(w_small), ptr(g_h0_next),
-                                  ptr(remap), ptr(self.saved[i]), cap, ptr(lay["mask"]), ptr(layer.W_h.weight),
-                                  ptr(w_ih), ptr(w_hh), self.act_code, int(has_h0), ptr(G4), ptr(g_pre), ptr(g_agg),
-                                  ptr(g_h0), st()))
-            wg = e(self.wg_out_floats)
+            check(lib.rg_node_bwd(d, cap, ptr(lay["n_dev"]), ptr(g_hid_e), ptr(g_small), g_small_stride, ptr(w_small),
+                                  w_rows, ptr(g_h0_next), ptr(remap), ptr(self.saved[i]), cap, ptr(lay["mask"]),
+                                  ptr(layer.W_h.weight), ptr(w_ih), ptr(w_hh), self.act_code, int(has_h0), ptr(G4),
+                                  ptr(g_pre), ptr(g_agg), ptr(g_h0), st()))
             check(lib.rg_node_wgrad(d, cap, ptr(lay["n_dev"]), ptr(self.saved[i]), cap, ptr(lay["mask"]),
                                     ptr(self.agg[i]), ptr(self.hidden[i]), ptr(G4), ptr(g_pre), ptr(g_small),
-                                    int(has_h0), ptr(self.wg_partial), ptr(wg), st()))
+                                    g_small_stride, int(has_h0), ptr(self.wg_partial), None,
+                                    ptr(gv["gate.weight_ih_l0"]), ptr(gv["gate.weight_hh_l0"]),
+                                    ptr(gv["gate.bias_ih_l0"]), ptr(gv["gate.bias_hh_l0"]), ptr(gv[pre + "W_h.weight"]),
+                                    ptr(ws_dst), w_rows, st()))
             _lib.Stats.launches += 3
-            d_wih += wg[:O_WHH].view(3 * d, d)
-            d_whh += wg[O_WHH:O_WH].view(3 * d, d)
-            grads[pre + "W_h.weight"] = wg[O_WH:O_WS].view(d, d)
-            b4 = wg[O_B:].view(4, d)                             # column sums of g_r', g_z', g_n', g_n' r
-            d_bih += b4[:3].reshape(-1)
-            d_bhh += torch.cat([b4[0], b4[1], b4[3]])
-            dws = wg[O_WS:O_B].view(8, d)                        # g_small^T hidden of this layer
-            if i == self.n_layer - 1:
-                grads["W_final.weight"] = dws[:1]
-            else:
-                grads["gnn_layers.%d.Ws_attn.weight" % (i + 1)] = dws[:a]
             # fused edge backward on the same implicit segments (grouped by the layer's INPUT nodes)
             hidden_prev = lay["hidden_prev"]
             bwd_seg, rela = lay["bwd_seg"], lay["rela"]
+            rows = rela.shape[0]
             cap_in = cap if i > 0 else n
             node_small = e(cap_in, 24)                           # every consumer stops at the true input-node count
             g_hid_e = e(cap_in, d) if hidden_prev is not None else None
-            copies = _lib.GRAD_COPIES
-            g_rela, g_ar8 = z(copies, rela.shape[0], d), z(copies, rela.shape[0], 8)
+            acc = z(copies * rows * (d + 8))                     # relation-gradient accumulator copies (atomics)
+            g_rela_c, g_ar8_c = acc[:copies * rows * d], acc[copies * rows * d:]
             heavy = _Heavy(bwd_seg.heavy_bound, d + 24, dev)
             check(lib.rg_edge_agg_bwd(C.byref(bwd_seg.c_struct()), d, ptr(hidden_prev), ptr(lay["as8"]), ptr(rela),
                                       ptr(lay["ar8"]), ptr(lay["aq8"]), ptr(lay["w8"]), ptr(layer.w_alpha.bias),
-                                      ptr(g_agg), ptr(g_hid_e), ptr(node_small), ptr(g_rela), ptr(g_ar8), copies,
+                                      ptr(g_agg), ptr(g_hid_e), ptr(node_small), ptr(g_rela_c), ptr(g_ar8_c), copies,
                                       heavy.ref(), st()))
-            g_rela, g_ar8 = g_rela.sum(0), g_ar8.sum(0)
             lay["heavy_bwd"] = heavy
-            _lib.Stats.launches += 1 + (3 if heavy.struct is not None else 1)      # + query sum
             q_part = e(n, 32, 24)
             check(lib.rg_query_sum8(n, ptr(node_small), ptr(lay["fr_in"].qinfo), ptr(q_part), st()))
-            q_sum = q_part.sum(1)                            # [n, 24] per-query sums of node_small
-            g_aq8 = q_sum[:, :8].contiguous()
-            tot = q_sum.sum(0)
-            grads[pre + "w_alpha.weight"] = tot[8:8 + a].reshape(1, a)
-            grads[pre + "w_alpha.bias"] = tot[16:17]
-            grads[pre + "Wr_attn.weight"] = (g_ar8.t() @ rela)[:a]
-            grads[pre + "Wqr_attn.weight"] = (g_aq8.t() @ lay["hq"])[:a]
-            grads[pre + "Wqr_attn.bias"] = g_aq8.sum(0)[:a]
-            g_rela = g_rela + g_ar8 @ lay["Wr8"] + self.onehot.t() @ (g_aq8 @ lay["Wqr8"])
-            grads[pre + "rela_embed.weight"] = g_rela
+            check(lib.rg_attn_param_grads(d, a, rows, n, copies, ptr(rela), ptr(layer.Wr_attn.weight),
+                                          ptr(layer.Wqr_attn.weight), ptr(self.rel), ptr(g_rela_c), ptr(g_ar8_c),
+                                          ptr(q_part), 32, ptr(gv[pre + "rela_embed.weight"]),
+                                          ptr(gv[pre + "Wr_attn.weight"]), ptr(gv[pre + "Wqr_attn.weight"]),
+                                          ptr(gv[pre + "Wqr_attn.bias"]), ptr(gv[pre + "w_alpha.weight"]),
+                                          ptr(gv[pre + "w_alpha.bias"]), st()))
+            _lib.Stats.launches += 2 + (3 if heavy.struct is not None else 1)
             if hidden_prev is not None:
-                # upstream of layer i-1 = edge part (g_hid_e) + attention-projection part (g_as8 . Ws_attn) +
-                # GRU-state part (g_h0 gathered through old_nodes_new_idx): all three summed inside rg_node_bwd
-                g_small = node_small[:, :8].contiguous()
-                w_small = lay["Ws8"].contiguous()
+                # upstream of layer i-1 = edge part (g_hid_e) + attention-projection part (g_as8 . Ws_attn, g_as8 =
+                # columns 0..7 of node_small) + GRU-state part (g_h0 gathered through old_nodes_new_idx): all three
+                # are summed inside rg_node_bwd; rg_node_wgrad of layer i-1 turns g_as8 into this layer's Ws_attn gradient
+                g_small, g_small_stride, w_small, w_rows = node_small, 24, layer.Ws_attn.weight, a
+                ws_dst = gv[pre + "Ws_attn.weight"]
                 g_h0_next, remap = g_h0, lay["remap"]
-        grads["gnn_layers.0.Ws_attn.weight"] = torch.zeros_like(m.gnn_layers[0].Ws_attn.weight)   # explicit zero (layer 0)
-        grads["gate.weight_ih_l0"], grads["gate.weight_hh_l0"] = d_wih, d_whh
-        grads["gate.bias_ih_l0"], grads["gate.bias_hh_l0"] = d_bih, d_bhh
-        for k in self.names:
-            self.grad_views[k].copy_(grads[k])
+        # layer 0 multiplies Ws_attn by an all-zero hidden: its gradient is an explicit zero (flat_grad.zero_ above)
 
     # ------------------------------------------------------------------------------------------
     def _build(self):

@@ -106,16 +106,16 @@ def test_node_backward_native_kernels_vs_fp64_autograd(d, n, act, has_h0, drop, 
     saved = torch.empty(6, pl, device=dev)
     check(lib.rg_node_update_train(d, n, None, ptr(agg), ptr(h_prev), ptr(src), ptr(W_h), ptr(gru.weight_ih_l0),
                                    ptr(gru.weight_hh_l0), ptr(gru.bias_ih_l0), ptr(gru.bias_hh_l0), act, ptr(mask),
-                                   ptr(hidden), ptr(saved), None, None, None, None, stream_ptr()))
+                                   ptr(hidden), ptr(saved), None, 0, None, None, None, stream_ptr()))
     e = lambda *s: torch.empty(*s, device=dev)
     G4, g_pre, g_agg, g_h0 = e(4, pl), e(pl), e(n, d), (e(n, d) if has_h0 else None)
-    check(lib.rg_node_bwd(d, n, None, ptr(g_hidden), ptr(g_small), ptr(w_small), ptr(g_h0_next), ptr(remap), ptr(saved), n,
+    check(lib.rg_node_bwd(d, n, None, ptr(g_hidden), ptr(g_small), 8, ptr(w_small), 8, ptr(g_h0_next), ptr(remap), ptr(saved), n,
                           ptr(mask), ptr(W_h), ptr(gru.weight_ih_l0), ptr(gru.weight_hh_l0), act, int(has_h0), ptr(G4),
                           ptr(g_pre), ptr(g_agg), ptr(g_h0), stream_ptr()))
     out_floats = int(lib.rg_node_wgrad_out_floats(d))
     partial, wg = e(int(lib.rg_node_wgrad_ctas()) * out_floats), e(out_floats)
-    check(lib.rg_node_wgrad(d, n, None, ptr(saved), n, ptr(mask), ptr(agg), ptr(hidden), ptr(G4), ptr(g_pre), ptr(g_small),
-                            int(has_h0), ptr(partial), ptr(wg), stream_ptr()))
+    check(lib.rg_node_wgrad(d, n, None, ptr(saved), n, ptr(mask), ptr(agg), ptr(hidden), ptr(G4), ptr(g_pre), ptr(g_small), 8,
+                            int(has_h0), ptr(partial), ptr(wg), None, None, None, None, None, None, 0, stream_ptr()))
     torch.cuda.synchronize()
     # fp64 autograd of the same op
     dd = lambda t: t.detach().double().requires_grad_(True)
@@ -155,7 +155,7 @@ def test_node_backward_native_kernels_vs_fp64_autograd(d, n, act, has_h0, drop, 
     # device-side count: rows past n_true are neither read nor written, weight gradients cover n_true rows only
     n_true = torch.tensor([n // 3], dtype=torch.int64, device=dev)
     g_agg2 = torch.full_like(g_agg, 7.0)
-    check(lib.rg_node_bwd(d, n, ptr(n_true), ptr(g_hidden), ptr(g_small), ptr(w_small), ptr(g_h0_next), ptr(remap), ptr(saved),
+    check(lib.rg_node_bwd(d, n, ptr(n_true), ptr(g_hidden), ptr(g_small), 8, ptr(w_small), 8, ptr(g_h0_next), ptr(remap), ptr(saved),
                           n, ptr(mask), ptr(W_h), ptr(gru.weight_ih_l0), ptr(gru.weight_hh_l0), act, int(has_h0), ptr(G4),
                           ptr(g_pre), ptr(g_agg2), ptr(g_h0), stream_ptr()))
     assert torch.equal(g_agg2[:n // 3], g_agg[:n // 3]) and float((g_agg2[n // 3:] - 7.0).abs().max()) == 0.0
