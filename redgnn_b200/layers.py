@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .ops import (Segments, edge_aggregate, edge_agg_forward, node_update, scatter_scores, ACT_CODES,
-                  NodeUpdateTrain)
+                  NodeUpdateTrain, attn_tables)
 
 SUPPORTED_DIMS = (16, 32, 48, 64)
 
@@ -235,9 +235,7 @@ class RedGNN(torch.nn.Module):
             fwd_seg.frontier = fr_next                    # lets bench.py resolve E / N' after the fact
             layer = self.gnn_layers[i]
             rela = layer.rela_embed.weight
-            ar8 = _pad8(layer.Wr_attn(rela)).contiguous()
-            aq8 = _pad8(layer.Wqr_attn(rela[q_rel])).contiguous()
-            w8 = _pad8(layer.w_alpha.weight).reshape(8).contiguous()
+            ar8, aq8, w8 = attn_tables(layer, q_rel)         # per-relation / per-query attention tables, one kernel
             agg = edge_agg_forward(fwd_seg, hidden, as8, rela, ar8, aq8, w8, layer.w_alpha.bias)
             last = i == self.n_layer - 1
             ws_next = None if last else F.pad(self.gnn_layers[i + 1].Ws_attn.weight,

@@ -155,6 +155,22 @@ def edge_agg_backward(bwd_seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg, 
 ACT_CODES = {"idd": 0, "relu": 1, "tanh": 2}
 
 
+def attn_tables(layer, q_rel):
+    """Inference: (ar8 [2R+1, 8], aq8 [n, 8], w8 [8]) of a GNNLayer in one kernel (rg_attn_tables):
+    Wr_attn(rela_embed), Wqr_attn(rela_embed[q_rel]) + bias, w_alpha -- models.py:29-36, factorised."""
+    rela = layer.rela_embed.weight
+    rows, d = rela.shape
+    n, a = q_rel.shape[0], layer.attn_dim
+    ar8 = torch.empty((rows, 8), dtype=torch.float32, device=rela.device)
+    aq8 = torch.empty((n, 8), dtype=torch.float32, device=rela.device)
+    w8 = torch.empty(8, dtype=torch.float32, device=rela.device)
+    check(lib.rg_attn_tables(d, a, rows, n, ptr(rela), ptr(layer.Wr_attn.weight), ptr(layer.Wqr_attn.weight),
+                             ptr(layer.Wqr_attn.bias), ptr(layer.w_alpha.weight), ptr(q_rel.contiguous()), ptr(ar8),
+                             ptr(aq8), ptr(w8), stream_ptr()))
+    _lib.Stats.launches += 1
+    return ar8, aq8, w8
+
+
 def scatter_scores(node_b, node_e, score, n_query, n_ent_out, n_dev=None):
     """scores_all (n, n_ent) with exact zeros for unvisited entities (rg_scatter_scores)."""
     out = torch.zeros((n_query, n_ent_out), dtype=torch.float32, device=score.device)
