@@ -288,12 +288,20 @@ class CpuReference(object):
 
 
 def timed_cpu_sample(ref, nq, budget_s, min_reps=3, max_reps=50):
-    ref.step(ref.queries(0, nq))                                        # warm-up
+    """Bounded sample of CPU steps.  The first step doubles as warm-up unless it alone exceeds the budget
+    (the 1 M-entity shapes take minutes per query on the host): then it IS the sample."""
+    t0 = time.perf_counter()
+    edges0 = ref.step(ref.queries(0, nq))
+    first = time.perf_counter() - t0
+    if first >= budget_s:
+        return 1, edges0, first
     t0 = time.perf_counter()
     reps, edges = 0, 0
     while reps < min_reps or (time.perf_counter() - t0 < budget_s and reps < max_reps):
         edges += ref.step(ref.queries(reps + 1, nq))
         reps += 1
+        if reps < min_reps and (time.perf_counter() - t0) > 3 * budget_s:
+            break
     return reps, edges, time.perf_counter() - t0
 
 
@@ -622,9 +630,9 @@ def kernel_breakdown(timing, steps):
 
 
 def measure_expand(B, mode, batch, subs0):
-    """Subsystem (1): the drop-in get_neighbors chain (explicit sampled_edges / tail_nodes / remap emission,
-    reference load_data.py:106-131) over one batch, device time per hop between CUDA events (the
-    16-byte count read-back between them is excluded).  Bytes: SURVEY 8(d) B_exp."""
+    """Subsystem (1): the drop-in get_neighbors (explicit sampled_edges / tail_nodes / remap emission,
+    reference load_data.py:106-131) hop by hop over one batch, device time of the two phases of a hop
+    between CUDA events (the 16-byte count read-back between them is excluded).  Bytes: SURVEY 8(d) B_exp."""
     dev = B.dev
     kg = B.loader.graph_for(mode, dev)
     exp_ms, exp_emit_ms, exp_bytes, exp_edges = 0.0, 0.0, 0.0, 0
@@ -632,28 +640,17 @@ def measure_expand(B, mode, batch, subs0):
         nodes = torch.stack([torch.arange(batch, device=dev), subs0], 1)
         spans = []
         for l in range(B.n_layer):
-            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
-            e0.record()
-            fr_in = kg.frontier_from_nodes(nodes, batch)
-            fr_out = kg.step(fr_in)
-            e1.record()
-            n_in, n_e, n_out, _ = fr_out.read_counts(also=fr_in)
-            if (n_e + n_out) * 48 > (40 << 30):           # keep the explicit edge list within HBM
+            if l and (spans[-1][2] + spans[-1][3]) * 48 * 4 > (40 << 30):   # keep the explicit edge list within HBM
                 break
-            e2.record()
-            tail_nodes = fr_out.nodes64(n_out)
-            remap = fr_in.remap_to(fr_out, n_in)
-            edges = kg.emit_edges(fr_in, fr_out, n_e)
-            e3.record()
-            spans.append((e0, e1, e2, e3, 56 * n_e + 4 * kg.n_fact + 24 * n_in + 16 * n_out, n_e))
+            tail_nodes, edges, remap = kg.get_neighbors(nodes, batch, spans=spans)
             nodes = tail_nodes
             del edges, remap
         torch.cuda.synchronize()
         if rep == 1:
-            for e0, e1, e2, e3, nbytes, n_e in spans:
-                exp_ms += e0.elapsed_time(e1) + e2.elapsed_time(e3)
-                exp_emit_ms += e2.elapsed_time(e3)
-                exp_bytes += nbytes
+            for ev, n_in, n_e, n_out in spans:
+                exp_ms += ev[0].elapsed_time(ev[1]) + ev[2].elapsed_time(ev[3])
+                exp_emit_ms += ev[2].elapsed_time(ev[3])
+                exp_bytes += 56 * n_e + 4 * kg.n_fact + 24 * n_in + 16 * n_out
                 exp_edges += n_e
     return exp_ms, exp_emit_ms, exp_bytes, exp_edges
 
@@ -754,8 +751,8 @@ def main():
                      "timing": "CUDA events around every rg_edge_agg_fwd launch, instrumented pass over the same batches",
                      "bytes_model": "(16+4d)*E + 4d*N' per launch (16*E + 4d*N' at layer 0)"},
         "subsystems": {
-            "expand": {"kernels": "rg_frontier_from_nodes + rg_frontier_step + rg_frontier_nodes + rg_frontier_remap "
-                                  "+ rg_edges_emit (explicit get_neighbors outputs, %d hops, one batch)" % B.n_layer,
+            "expand": {"kernels": "DataLoader.get_neighbors = rg_get_neighbors_expand + rg_get_neighbors_emit "
+                                  "(explicit tail_nodes / sampled_edges / old_nodes_new_idx, %d hops, one batch)" % B.n_layer,
                        "ms": exp_ms, "ms_emit_part": exp_emit_ms, "edges": exp_edges, "achieved": gbps(exp_bytes, exp_ms),
                        "peak": peak, "unit": "GB/s", "frac": gbps(exp_bytes, exp_ms) / peak,
                        "bytes_model": "56*E + 4*n_fact + 24*N + 16*N' per hop"},

@@ -185,6 +185,17 @@ int rg_frontier_remap(const rg_frontier *in, const rg_frontier *out, int64_t *re
 int rg_edges_emit(const rg_graph *g, const rg_frontier *in, const rg_frontier *out,
                   const void *ws, size_t ws_bytes, int64_t n_edges, int64_t *edges, void *stream);
 
+/* The public get_neighbors hop (load_data.py:106-131) as two calls around the one count read-back:
+ * rg_get_neighbors_expand = rg_frontier_from_nodes + rg_frontier_step (counts_in / counts_out as above),
+ * rg_get_neighbors_emit   = rg_frontier_nodes (tail_nodes [N'][2]) + rg_frontier_remap (old_nodes_new_idx
+ *                           [N]) + rg_edges_emit (sampled_edges [E][6]), all int64. */
+int rg_get_neighbors_expand(const rg_graph *g, const int64_t *nodes, int64_t n_nodes, rg_frontier *in,
+                            rg_frontier *out, int64_t *counts_in, int64_t *counts_out, void *ws,
+                            size_t ws_bytes, void *stream);
+int rg_get_neighbors_emit(const rg_graph *g, const rg_frontier *in, const rg_frontier *out, const void *ws,
+                          size_t ws_bytes, int64_t n_edges, int64_t *tail_nodes, int64_t *edges,
+                          int64_t *old_nodes_new_idx, void *stream);
+
 /* ---- propagation: GNNLayer.forward (transductive/models.py:23-43) and its autograd ------------
  * Attention is factorised: as8[N][8] = hidden @ Ws^T, ar8[2R+1][8] = rela @ Wr^T,
  * aq8[n][8] = rela[q_rel] @ Wqr^T + b_qr (columns >= attn_dim are zero), w8[8] = w_alpha (zero

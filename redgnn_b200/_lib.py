@@ -59,6 +59,11 @@ SIGNATURES = {
     "rg_frontier_nodes": (C.c_int, [C.POINTER(RgFrontier), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rg_frontier_remap": (C.c_int, [C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
+    "rg_get_neighbors_expand": (C.c_int, [C.POINTER(RgGraph), C.c_void_p, C.c_int64, C.POINTER(RgFrontier),
+                                          C.POINTER(RgFrontier), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.c_void_p]),
+    "rg_get_neighbors_emit": (C.c_int, [C.POINTER(RgGraph), C.POINTER(RgFrontier), C.POINTER(RgFrontier), C.c_void_p,
+                                        C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rg_node_update": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 11 + [C.c_int32] + [C.c_void_p] * 4),
     "rg_node_update_train": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 9 + [C.c_int32] + [C.c_void_p] * 4
                              + [C.c_int32] + [C.c_void_p] * 4),

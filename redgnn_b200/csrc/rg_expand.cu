@@ -325,9 +325,57 @@ int check_frontier(const rg_frontier *fr) {
     return RG_OK;
 }
 
+// Small dictionaries (every shape but the widest batches): ONE CTA walks all words with a running block
+// scan and also writes the per-query {base, count} -- one launch instead of reduce + scan + apply +
+// query-info (a hop is a chain of ~3 us kernels; on small KGs and in the Python-driven public
+// get_neighbors their launch latency is most of the hop).
+constexpr int64_t kSmallDictWords = 512 * 1024;
+__global__ void __launch_bounds__(1024) k_dict_prefix_small(uint32_t *dict, int64_t n_words, int n_query, int We,
+                                                            int64_t *count_out, int32_t *qinfo) {
+    __shared__ uint32_t sm[1024 / 32 + 1];
+    constexpr int IPT = 4;
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < n_words; base += 1024 * IPT) {
+        const int64_t first = base + (int64_t)threadIdx.x * IPT;
+        uint32_t c[IPT], s = 0;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int64_t i = first + k;
+            c[k] = (i < n_words) ? __popc(dict[2 * i]) : 0;
+            s += c[k];
+        }
+        uint32_t tot;
+        uint32_t run = carry + rg_block_exclusive_scan<1024>(s, sm, tot);
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const int64_t i = first + k;
+            if (i < n_words) {
+                dict[2 * i + 1] = run;
+                if (qinfo && i % We == 0) qinfo[2 * (i / We)] = (int32_t)run;   // first word of a query's row
+            }
+            run += c[k];
+        }
+        carry += tot;
+    }
+    if (threadIdx.x == 0 && count_out) *count_out = (int64_t)carry;
+    if (qinfo) {
+        __syncthreads();
+        for (int q = threadIdx.x; q < n_query; q += 1024) {
+            const int32_t b0 = qinfo[2 * q], b1 = (q + 1 < n_query) ? qinfo[2 * (q + 1)] : (int32_t)carry;
+            qinfo[2 * q + 1] = b1 - b0;
+        }
+    }
+}
+
 // dictionary bits -> rank prefixes; total written to counts[which]
 int dict_prefix(const rg_frontier *fr, const RgWorkspace &w, int64_t *count_out, cudaStream_t st) {
     const int64_t n_words = (int64_t)fr->n_query * rg_words_ent(fr->n_ent);
+    if (n_words <= kSmallDictWords) {
+        k_dict_prefix_small<<<1, 1024, 0, st>>>(fr->dict, n_words, fr->n_query, rg_words_ent(fr->n_ent), count_out,
+                                              fr->qinfo);
+        RG_LAUNCH_CHECK();
+        return RG_OK;
+    }
     const int64_t nb = rg_cdiv(n_words, RG_TILE);
     k_dict_reduce<<<(unsigned)nb, kBlock, 0, st>>>(fr->dict, n_words, w.dict_blocksum);
     RG_LAUNCH_CHECK();
@@ -456,6 +504,25 @@ int rg_edges_emit(const rg_graph *g, const rg_frontier *in, const rg_frontier *o
                                                     in->n_query, in->n_ent, w.fact_blockprefix, edges);
     RG_LAUNCH_CHECK();
     return RG_OK;
+}
+
+// ---- the public get_neighbors hop as TWO calls (one count read-back in between) -----------------------
+// Driven from Python every C call costs ~10 us of host time; a hop was five calls.
+int rg_get_neighbors_expand(const rg_graph *g, const int64_t *nodes, int64_t n_nodes, rg_frontier *in, rg_frontier *out,
+                            int64_t *counts_in, int64_t *counts_out, void *ws, size_t ws_bytes, void *stream) {
+    int rc = rg_frontier_from_nodes(nodes, n_nodes, in, counts_in, ws, ws_bytes, stream);
+    if (rc) return rc;
+    return rg_frontier_step(g, in, out, counts_out, ws, ws_bytes, stream);
+}
+
+int rg_get_neighbors_emit(const rg_graph *g, const rg_frontier *in, const rg_frontier *out, const void *ws,
+                          size_t ws_bytes, int64_t n_edges, int64_t *tail_nodes, int64_t *edges,
+                          int64_t *old_nodes_new_idx, void *stream) {
+    int rc = rg_frontier_nodes(out, tail_nodes, nullptr, nullptr, stream);
+    if (rc) return rc;
+    rc = rg_frontier_remap(in, out, old_nodes_new_idx, nullptr, nullptr, stream);
+    if (rc) return rc;
+    return rg_edges_emit(g, in, out, ws, ws_bytes, n_edges, edges, stream);
 }
 
 }  // extern "C"

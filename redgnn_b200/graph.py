@@ -158,7 +158,7 @@ class DeviceGraph(object):
         ws = self.workspace(n_query)
         check(lib.rg_frontier_from_nodes(ptr(nodes64), nodes64.shape[0], C.byref(fr.c_struct()), ptr(fr.counts),
                                          ptr(ws), ws.numel(), stream_ptr()))
-        _lib.Stats.launches += 5      # k_set_nodes + dict reduce / scan / apply + query info
+        _lib.Stats.launches += 1 + self._dict_launches(n_query)      # k_set_nodes + dictionary prefix
         return fr
 
     def step(self, fr_in):
@@ -168,8 +168,12 @@ class DeviceGraph(object):
         ws = self.workspace(fr_in.n_query)
         check(lib.rg_frontier_step(C.byref(self.c_struct()), C.byref(fr_in.c_struct()), C.byref(fr_out.c_struct()),
                                    ptr(fr_out.counts), ptr(ws), ws.numel(), stream_ptr()))
-        _lib.Stats.launches += 7      # fact_count, scan, transpose, dict reduce / scan / apply, query info
+        _lib.Stats.launches += 3 + self._dict_launches(fr_in.n_query)   # fact_count, scan, transpose + dictionary prefix
         return fr_out
+
+    def _dict_launches(self, n_query):
+        """Kernels of the dictionary-prefix step: one for small dictionaries (k_dict_prefix_small), else four."""
+        return 1 if n_query * ((self.n_ent + 31) // 32) <= 512 * 1024 else 4
 
     def emit_edges(self, fr_in, fr_out, n_edges):
         edges = torch.empty((n_edges, 6), dtype=torch.int64, device=self.device)
@@ -179,10 +183,11 @@ class DeviceGraph(object):
         _lib.Stats.launches += 1
         return edges
 
-    def get_neighbors(self, nodes, n_query=None):
+    def get_neighbors(self, nodes, n_query=None, spans=None):
         """Drop-in body of DataLoader.get_neighbors for this KG: returns cuda int64 tensors
         (tail_nodes[N',2], sampled_edges[E,6], old_nodes_new_idx[N]) bit-identical to the
-        reference's, in the reference's order."""
+        reference's, in the reference's order.  `spans` (bench.py): a list that receives CUDA events
+        around the two device phases of the hop and its sizes."""
         if isinstance(nodes, np.ndarray):
             if n_query is None:
                 n_query = int(nodes[:, 0].max()) + 1 if len(nodes) else 1
@@ -191,15 +196,34 @@ class DeviceGraph(object):
             nodes = nodes.to(device=self.device, dtype=torch.int64)
             if n_query is None:
                 n_query = int(nodes[:, 0].max().item()) + 1 if nodes.shape[0] else 1
-        fr_in = self.frontier_from_nodes(nodes, n_query)
-        fr_out = self.step(fr_in)
-        n_in, n_edges, n_out, err = fr_out.read_counts(also=fr_in)
-        if err:
-            raise _lib.RgError("get_neighbors: node out of range (batch_idx >= %d or entity >= %d)"
-                               % (n_query, self.n_ent))
-        tail_nodes = fr_out.nodes64(n_out)
-        remap = fr_in.remap_to(fr_out, n_in)
-        edges = self.emit_edges(fr_in, fr_out, n_edges)
+        nodes = nodes.contiguous()
+        fr_in, fr_out = self.new_frontier(n_query), self.new_frontier(n_query)
+        ws = self.workspace(n_query)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if spans is not None else None
+        with torch.cuda.device(self.device):
+            if ev:
+                ev[0].record()
+            check(lib.rg_get_neighbors_expand(C.byref(self.c_struct()), ptr(nodes), nodes.shape[0],
+                                              C.byref(fr_in.c_struct()), C.byref(fr_out.c_struct()), ptr(fr_in.counts),
+                                              ptr(fr_out.counts), ptr(ws), ws.numel(), stream_ptr()))
+            if ev:
+                ev[1].record()
+            n_in, n_edges, n_out, err = fr_out.read_counts(also=fr_in)      # the one host synchronisation of a hop
+            if err:
+                raise _lib.RgError("get_neighbors: node out of range (batch_idx >= %d or entity >= %d)"
+                                   % (n_query, self.n_ent))
+            tail_nodes = torch.empty((n_out, 2), dtype=torch.int64, device=self.device)
+            edges = torch.empty((n_edges, 6), dtype=torch.int64, device=self.device)
+            remap = torch.empty(n_in, dtype=torch.int64, device=self.device)
+            if ev:
+                ev[2].record()
+            check(lib.rg_get_neighbors_emit(C.byref(self.c_struct()), C.byref(fr_in.c_struct()), C.byref(fr_out.c_struct()),
+                                            ptr(ws), ws.numel(), n_edges, ptr(tail_nodes), ptr(edges), ptr(remap),
+                                            stream_ptr()))
+            if ev:
+                ev[3].record()
+                spans.append((ev, n_in, n_edges, n_out))
+        _lib.Stats.launches += 4 + 2 * self._dict_launches(n_query) + 3
         return tail_nodes, edges, remap
 
 
