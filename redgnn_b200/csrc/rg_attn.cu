@@ -38,8 +38,14 @@ __global__ void __launch_bounds__(256) k_attn_tables(int D, int A, int rows, int
     }
 }
 
-// one CTA: every parameter gradient of a layer's attention / relation side, written in place
-constexpr int kPgThreads = 1024;
+// Every parameter gradient of a layer's attention / relation side, written in place.  CTAs 0 .. R-1 own
+// kPgRows relation rows each (rela_embed.weight rows: sum of the accumulator copies + g_ar8 . Wr + the query
+// part, queries in ascending order => deterministic); the LAST CTA computes the small tensors (Wr_attn,
+// Wqr_attn weight / bias, w_alpha weight / bias), which need reductions over ALL rows / queries.
+// (One CTA for everything took 81 us per layer: 8 copies x 475 rows x 48 floats read by 1024 threads.)
+constexpr int kPgThreads = 512;
+constexpr int kPgRows = 16;
+
 __global__ void __launch_bounds__(kPgThreads) k_attn_param_grads(
     int D, int A, int rows, int n, int copies, const float *__restrict__ rela, const float *__restrict__ Wr,
     const float *__restrict__ Wqr, const int64_t *__restrict__ q_rel, const float *__restrict__ g_rela_c,
@@ -47,15 +53,10 @@ __global__ void __launch_bounds__(kPgThreads) k_attn_param_grads(
     float *__restrict__ g_Wr, float *__restrict__ g_Wqr, float *__restrict__ g_bqr, float *__restrict__ g_w_alpha,
     float *__restrict__ g_b_alpha) {
     extern __shared__ float sm[];
-    float *s_gar = sm;                      // [rows][8]  sum over copies of g_ar8
-    float *s_gaq = s_gar + (size_t)rows * 8;  // [n][8]     per-query sums of g_as8 (= g_aq8)
-    float *s_w = s_gaq + (size_t)n * 8;       // [2][8][D]  Wr, Wqr (zero rows above A)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < rows * 8; i += kPgThreads) {
-        float s = 0.f;
-        for (int c = 0; c < copies; ++c) s += __ldg(g_ar8_c + (size_t)c * rows * 8 + i);
-        s_gar[i] = s;
-    }
+    float *s_gaq = sm;                        // [n][8]     per-query sums of g_as8 (= g_aq8)
+    float *s_w = s_gaq + (size_t)n * 8;       // [2][8][D]  Wr, Wqr (zero rows above A)
+    float *s_gar = s_w + 16 * D;              // [rows or kPgRows][8]  sum over copies of g_ar8
     for (int i = tid; i < n * 8; i += kPgThreads) {
         const int b = i >> 3, k = i & 7;
         float s = 0.f;
@@ -65,6 +66,39 @@ __global__ void __launch_bounds__(kPgThreads) k_attn_param_grads(
     for (int i = tid; i < 2 * 8 * D; i += kPgThreads) {
         const int which = i / (8 * D), k = (i / D) & 7, c = i % D;
         s_w[i] = k < A ? __ldg((which ? Wqr : Wr) + k * D + c) : 0.f;
+    }
+    const int n_row_ctas = gridDim.x - 1;
+    if ((int)blockIdx.x < n_row_ctas) {
+        // ---- rela_embed.weight rows [r0, r1) ----
+        const int r0 = blockIdx.x * kPgRows, r1 = min(rows, r0 + kPgRows), nr = r1 - r0;
+        for (int i = tid; i < nr * 8; i += kPgThreads) {
+            float s = 0.f;
+            for (int c = 0; c < copies; ++c) s += __ldg(g_ar8_c + (size_t)c * rows * 8 + (size_t)r0 * 8 + i);
+            s_gar[i] = s;
+        }
+        __syncthreads();
+        for (int i = tid; i < nr * D; i += kPgThreads) {
+            const int rl = i / D, c = i % D, r = r0 + rl;
+            float s = 0.f;
+            for (int cp = 0; cp < copies; ++cp) s += __ldg(g_rela_c + ((size_t)cp * rows + r) * D + c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = fmaf(s_gar[rl * 8 + k], s_w[k * D + c], s);
+            for (int b = 0; b < n; ++b) {           // + g_aq8[b] . Wqr[:, c] for the queries whose relation is r
+                if ((int)q_rel[b] != r) continue;
+                float t = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t = fmaf(s_gaq[b * 8 + k], s_w[8 * D + k * D + c], t);
+                s += t;
+            }
+            g_rela[(size_t)r * D + c] = s;
+        }
+        return;
+    }
+    // ---- last CTA: the small tensors ----
+    for (int i = tid; i < rows * 8; i += kPgThreads) {
+        float s = 0.f;
+        for (int c = 0; c < copies; ++c) s += __ldg(g_ar8_c + (size_t)c * rows * 8 + i);
+        s_gar[i] = s;
     }
     // w_alpha.weight / bias: columns 8..8+A and 16 of the per-query partial sums, one warp per column
     if (warp < 9) {
@@ -83,41 +117,29 @@ __global__ void __launch_bounds__(kPgThreads) k_attn_param_grads(
     }
     __syncthreads();
     // Wr_attn.weight[k][c] = sum_r g_ar8[r][k] rela[r][c];  Wqr_attn.weight[k][c] = sum_b g_aq8[b][k] rela[q_rel[b]][c]
-    if (tid < A * D) {
-        const int k = tid / D, c = tid % D;
+    for (int o = tid; o < 2 * A * D; o += kPgThreads) {
+        const bool second = o >= A * D;
+        const int j = second ? o - A * D : o, k = j / D, c = j % D;
         float s = 0.f;
-        for (int r = 0; r < rows; ++r) s = fmaf(s_gar[r * 8 + k], __ldg(rela + (size_t)r * D + c), s);
-        g_Wr[tid] = s;
-    } else if (tid >= 512 && tid < 512 + A * D) {
-        const int j = tid - 512, k = j / D, c = j % D;
-        float s = 0.f;
-        for (int b = 0; b < n; ++b) s = fmaf(s_gaq[b * 8 + k], __ldg(rela + (size_t)q_rel[b] * D + c), s);
-        g_Wqr[j] = s;
-    }
-    if (tid >= kPgThreads - 32 && tid < kPgThreads - 32 + A) {   // Wqr_attn.bias[k] = sum_b g_aq8[b][k]
-        const int k = tid - (kPgThreads - 32);
-        float s = 0.f;
-        for (int b = 0; b < n; ++b) s += s_gaq[b * 8 + k];
-        g_bqr[k] = s;
-    }
-    // rela_embed.weight[r][c] = sum_copies g_rela + g_ar8[r] . Wr[:, c]   (+ the query part below)
-    for (int i = tid; i < rows * D; i += kPgThreads) {
-        const int r = i / D, c = i % D;
-        float s = 0.f;
-        for (int cp = 0; cp < copies; ++cp) s += __ldg(g_rela_c + (size_t)cp * rows * D + i);
+        if (!second) {
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+            int r = 0;
+            for (; r + 4 <= rows; r += 4) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s = fmaf(s_gar[r * 8 + k], s_w[k * D + c], s);
-        g_rela[i] = s;
-    }
-    __syncthreads();
-    // ... += g_aq8[b] . Wqr[:, c] into row q_rel[b]: queries in order by the same thread => deterministic
-    if (tid < D) {
-        for (int b = 0; b < n; ++b) {
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s = fmaf(s_gaq[b * 8 + k], s_w[8 * D + k * D + tid], s);
-            g_rela[(size_t)q_rel[b] * D + tid] += s;
+                for (int u = 0; u < 4; ++u) s4[u] = fmaf(s_gar[(r + u) * 8 + k], __ldg(rela + (size_t)(r + u) * D + c), s4[u]);
+            }
+            for (; r < rows; ++r) s4[0] = fmaf(s_gar[r * 8 + k], __ldg(rela + (size_t)r * D + c), s4[0]);
+            s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            g_Wr[j] = s;
+        } else {
+            for (int b = 0; b < n; ++b) s = fmaf(s_gaq[b * 8 + k], __ldg(rela + (size_t)q_rel[b] * D + c), s);
+            g_Wqr[j] = s;
         }
+    }
+    if (tid < A) {   // Wqr_attn.bias[k] = sum_b g_aq8[b][k]
+        float s = 0.f;
+        for (int b = 0; b < n; ++b) s += s_gaq[b * 8 + tid];
+        g_bqr[tid] = s;
     }
 }
 
@@ -150,7 +172,8 @@ extern "C" int rg_attn_param_grads(int32_t hidden_dim, int32_t attn_dim, int32_t
     const size_t smem = ((size_t)n_rows * 8 + (size_t)n_query * 8 + 16 * hidden_dim) * sizeof(float);
     if (smem > 200 * 1024) return RG_ERR_TOO_LARGE;
     RG_CUDA_CALL(cudaFuncSetAttribute(k_attn_param_grads, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_attn_param_grads<<<1, kPgThreads, smem, (cudaStream_t)stream>>>(
+    const unsigned grid = (unsigned)rg_cdiv(n_rows, kPgRows) + 1;
+    k_attn_param_grads<<<grid, kPgThreads, smem, (cudaStream_t)stream>>>(
         hidden_dim, attn_dim, n_rows, n_query, grad_copies, rela, Wr, Wqr, q_rel, g_rela_copies, g_ar8_copies, q_part,
         q_slices, g_rela, g_Wr, g_Wqr, g_bqr, g_w_alpha, g_b_alpha);
     RG_LAUNCH_CHECK();

@@ -325,11 +325,11 @@ int check_frontier(const rg_frontier *fr) {
     return RG_OK;
 }
 
-// Small dictionaries (every shape but the widest batches): ONE CTA walks all words with a running block
+// Tiny dictionaries (<= 8 K words: small KGs / small batches): ONE CTA walks all words with a running block
 // scan and also writes the per-query {base, count} -- one launch instead of reduce + scan + apply +
-// query-info (a hop is a chain of ~3 us kernels; on small KGs and in the Python-driven public
-// get_neighbors their launch latency is most of the hop).
-constexpr int64_t kSmallDictWords = 512 * 1024;
+// query-info.  (Beyond two passes of the CTA the four-kernel chain is faster again: measured on the
+// FB15k-237 shape, 29 K words, +20 us per hop inside the captured forward.)
+constexpr int64_t kSmallDictWords = 8 * 1024;
 __global__ void __launch_bounds__(1024) k_dict_prefix_small(uint32_t *dict, int64_t n_words, int n_query, int We,
                                                             int64_t *count_out, int32_t *qinfo) {
     __shared__ uint32_t sm[1024 / 32 + 1];

@@ -352,8 +352,9 @@ int launch_node_bwd(const float *g_hidden, const float *g_small, int g_small_str
 //   interleaved: ((i / 4) * 32 + k) * 4 + i % 4      row-major: k * width + i.
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgNodes = 32;   // nodes per ring stage = one lane-interleaved tile
-constexpr int kWgStages = 2;   // 2 x 57 KB per CTA: two CTAs per SM
-constexpr int kWgCtas = 148 * 2;
+constexpr int kWgStages = 3;   // 3 x <= 60 KB: one CTA per SM (two thread halves splitting a slab's rows were measured
+constexpr int kWgCtas = 148;   // slower: 0.61 -> 0.69 ms on the FB15k-237 training step)
+constexpr int kWgHalves = 1;
 
 struct WgLayout {   // float offsets of the sources inside one ring stage (-1 = source absent)
     int ox, om, oh, oa, ohid, og4, ogp, ogs, stage;
@@ -364,7 +365,8 @@ struct Wg {
     static constexpr int KS = kWgNodes;
     static constexpr int T1 = (D / 8) * (3 * D / 8), T3 = (D / 8) * (D / 8), T4 = D / 8, T5 = 4 * D / 8;
     static constexpr int TILES = 2 * T1 + T3 + T4 + T5;
-    static constexpr int THREADS = ((TILES + 31) / 32) * 32;
+    static constexpr int HALF = ((TILES + 31) / 32) * 32;   // threads of one half (one thread per register tile)
+    static constexpr int THREADS = kWgHalves * HALF;
     // output layout
     static constexpr int O_WIH = 0, O_WHH = 3 * D * D, O_WH = 6 * D * D, O_WS = 7 * D * D, O_B = 7 * D * D + 8 * D;
     static constexpr int OUT = O_B + 4 * D;
@@ -396,7 +398,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 }
 
 template <int D, bool HAS_H0>
-__global__ void __maxnreg__(112) k_node_wgrad(
+__global__ void __launch_bounds__(Wg<D>::THREADS, 1) k_node_wgrad(
     const float *__restrict__ saved, int64_t plane_rows, const float *__restrict__ drop_mask,
     const float *__restrict__ agg, const float *__restrict__ hidden, const float *__restrict__ G4,
     const float *__restrict__ g_pre, const float *__restrict__ g_small, int g_small_stride, int64_t n_nodes_host,
@@ -404,7 +406,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
     using W = Wg<D>;
     extern __shared__ __align__(128) float wg_smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(wg_smem + kWgStages * L.stage);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, half = tid / W::HALF;
     const int64_t n_nodes = n_nodes_dev ? *n_nodes_dev : n_nodes_host;
     const int64_t n_slabs = (n_nodes + kWgNodes - 1) / kWgNodes;
     const int64_t my_slabs = n_slabs > (int64_t)blockIdx.x ? (n_slabs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -417,7 +419,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
         constexpr int IB = D / 8;
         auto il = [](int base, int col) { return base + (col / 4) * kIlChunk; };   // interleaved: chunk offset, k * 4 added
         auto g4 = [&](int col) { return il(L.og4 + (col / D) * il_tile_floats(D), col % D); };
-        int t = tid;
+        int t = tid % W::HALF;
         if (t < W::T1) {
             xo = il(L.ox, 8 * (t % IB)), go = g4(8 * (t / IB));
             out = W::O_WIH + 8 * (t / IB) * D + 8 * (t % IB), kind = 0;
@@ -491,7 +493,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
             const float *xp = st + xo, *gp = st + go;
             if (mo >= 0) {
                 const float *mp = st + mo;
-                for (int k = 0; k < rows; ++k) {
+                for (int k = half; k < rows; k += kWgHalves) {
                     const float4 x0 = *reinterpret_cast<const float4 *>(xp + k * xk);
                     const float4 x1 = *reinterpret_cast<const float4 *>(xp + k * xk + xh);
                     const float4 m0 = *reinterpret_cast<const float4 *>(mp + k * D);
@@ -508,7 +510,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
                 }
             } else {
 #pragma unroll 4
-                for (int k = 0; k < rows; ++k) {
+                for (int k = half; k < rows; k += kWgHalves) {
                     const float4 x0 = *reinterpret_cast<const float4 *>(xp + k * xk);
                     const float4 x1 = *reinterpret_cast<const float4 *>(xp + k * xk + xh);
                     const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gk);
@@ -523,7 +525,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
             }
         } else if (kind == 1) {
             const float *gp = st + go;
-            for (int k = 0; k < rows; ++k) {
+            for (int k = half; k < rows; k += kWgHalves) {
                 const float4 g0 = *reinterpret_cast<const float4 *>(gp + k * gk);
                 const float4 g1 = *reinterpret_cast<const float4 *>(gp + k * gk + gh);
                 acc[0][0] += g0.x; acc[0][1] += g0.y; acc[0][2] += g0.z; acc[0][3] += g0.w;
@@ -536,7 +538,7 @@ __global__ void __maxnreg__(112) k_node_wgrad(
             issue(it + kWgStages);
         }
     }
-    float *po = partial + (size_t)blockIdx.x * W::OUT + out;
+    float *po = partial + ((size_t)blockIdx.x * kWgHalves + half) * W::OUT + out;
     if (kind == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -621,7 +623,7 @@ int launch_wgrad(const float *saved, int64_t plane_rows, const float *drop_mask,
     kern<<<grid, W::THREADS, smem, st>>>(saved, plane_rows, drop_mask, agg, hidden, G4, g_pre, g_small, g_small_stride,
                                         n_nodes, n_nodes_dev, partial, L);
     RG_LAUNCH_CHECK();
-    k_wgrad_reduce<D, HH><<<(W::OUT + 31) / 32, 256, 0, st>>>(partial, grid, g_small != nullptr, dst);
+    k_wgrad_reduce<D, HH><<<(W::OUT + 31) / 32, 256, 0, st>>>(partial, grid * kWgHalves, g_small != nullptr, dst);
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
@@ -660,7 +662,7 @@ extern "C" int rg_node_bwd(int32_t hidden_dim, int64_t n_nodes, const int64_t *n
 #undef RG_NB
 }
 
-extern "C" int32_t rg_node_wgrad_ctas(void) { return kWgCtas; }
+extern "C" int32_t rg_node_wgrad_ctas(void) { return kWgCtas * kWgHalves; }   // partial rows the caller provides
 
 extern "C" int64_t rg_node_wgrad_out_floats(int32_t hidden_dim) {
     switch (hidden_dim) {

@@ -173,7 +173,7 @@ class DeviceGraph(object):
 
     def _dict_launches(self, n_query):
         """Kernels of the dictionary-prefix step: one for small dictionaries (k_dict_prefix_small), else four."""
-        return 1 if n_query * ((self.n_ent + 31) // 32) <= 512 * 1024 else 4
+        return 1 if n_query * ((self.n_ent + 31) // 32) <= 8 * 1024 else 4
 
     def emit_edges(self, fr_in, fr_out, n_edges):
         edges = torch.empty((n_edges, 6), dtype=torch.int64, device=self.device)
