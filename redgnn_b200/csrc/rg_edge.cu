@@ -90,10 +90,12 @@ __device__ __forceinline__ SegRange seg_range(const rg_segments &S, int64_t seg)
 }
 
 // queue the chunks 1.. of a heavy segment (chunk 0 is done by the owner warp); warp-collective
+// `own` = slots the owner warp keeps for itself (defaults to one chunk)
 template <bool PUBLISH = false>
 __device__ __forceinline__ void enqueue_heavy(const rg_heavy &H, int64_t seg, int len, int lane,
-                                              int chunk = RG_HEAVY_CHUNK) {
-    const int nch = (len + chunk - 1) / chunk - 1;
+                                              int chunk = RG_HEAVY_CHUNK, int own = 0) {
+    if (own <= 0) own = chunk;
+    const int nch = (len - own + chunk - 1) / chunk;
     int base = 0, slot = 0;
     if (lane == 0) {
         base = atomicAdd(&H.counters[0], nch);
@@ -817,7 +819,7 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
                                                      const float *__restrict__ w8, const float *__restrict__ b_alpha,
                                                      const float *__restrict__ g_agg, float *g_hidden,
                                                      float *node_small, float *g_rela, float *g_ar8, int copies,
-                                                     rg_heavy H, int has_heavy) {
+                                                     rg_heavy H, int has_heavy, int own0) {
     const int lane = threadIdx.x & 31;
     select_copy<D>(g_rela, g_ar8, copies, S.n_table_rows);
     const int64_t n_true = S.n_seg_dev ? *S.n_seg_dev : S.n_seg;
@@ -827,9 +829,9 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
         if (seg >= n_true) return;
         SegRange r = seg_range<IMPLICIT>(S, seg);
         int hi = r.hi;
-        if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK_BWD) {  // without a queue the owner warp does it all
-            enqueue_heavy(H, seg, r.hi - r.lo, lane, RG_HEAVY_CHUNK_BWD);
-            hi = r.lo + RG_HEAVY_CHUNK_BWD;
+        if (has_heavy && r.hi - r.lo > own0) {  // without a queue the owner warp does it all
+            enqueue_heavy(H, seg, r.hi - r.lo, lane, RG_HEAVY_SUB_BWD, own0);
+            hi = r.lo + own0;
         }
         float4 G[D / 16];
         BwdSmall sm;
@@ -876,9 +878,9 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd(rg_segments S, const float 
         const int lo = __shfl_sync(RG_FULL_MASK, r.lo, src);
         int hi = __shfl_sync(RG_FULL_MASK, r.hi, src);
         const int64_t sg = seg0 + (src >> 2);
-        if (has_heavy && hi - lo > RG_HEAVY_CHUNK_BWD) {  // without a queue the owner warp does it all
-            enqueue_heavy(H, sg, hi - lo, lane, RG_HEAVY_CHUNK_BWD);
-            hi = lo + RG_HEAVY_CHUNK_BWD;
+        if (has_heavy && hi - lo > own0) {  // without a queue the owner warp does it all
+            enqueue_heavy(H, sg, hi - lo, lane, RG_HEAVY_SUB_BWD, own0);
+            hi = lo + own0;
         }
         bwd_range<D, HAS_HIDDEN, IMPLICIT>(S, sg, q, lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, g_agg, g_rela, g_ar8,
                                            G, sm);
@@ -899,7 +901,7 @@ __global__ void __launch_bounds__(kPWarpsB * 32, 2) k_edge_bwd_p(rg_segments S, 
                                                                const float *__restrict__ b_alpha,
                                                                const float *__restrict__ g_agg, float *g_hidden,
                                                                float *node_small, float *g_rela, float *g_ar8,
-                                                               int copies, rg_heavy H, int has_heavy) {
+                                                               int copies, rg_heavy H, int has_heavy, int own0) {
     extern __shared__ __align__(128) float s_tab[];
     __shared__ __align__(8) unsigned long long tab_bar;
     select_copy<D>(g_rela, g_ar8, copies, S.n_table_rows);
@@ -913,9 +915,9 @@ __global__ void __launch_bounds__(kPWarpsB * 32, 2) k_edge_bwd_p(rg_segments S, 
     for (int64_t seg = (int64_t)blockIdx.x * kPWarpsB + (threadIdx.x >> 5); seg < n_true; seg += stride) {
         SegRange r = seg_range<true>(S, seg);
         int hi = r.hi;
-        if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK_BWD) {
-            enqueue_heavy(H, seg, r.hi - r.lo, lane, RG_HEAVY_CHUNK_BWD);
-            hi = r.lo + RG_HEAVY_CHUNK_BWD;
+        if (has_heavy && r.hi - r.lo > own0) {
+            enqueue_heavy(H, seg, r.hi - r.lo, lane, RG_HEAVY_SUB_BWD, own0);
+            hi = r.lo + own0;
         }
         float4 G[D / 16];
         BwdSmall sm;
@@ -937,7 +939,7 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd_chunks(rg_segments S, const
                                                             const float *__restrict__ w8,
                                                             const float *__restrict__ b_alpha,
                                                             const float *__restrict__ g_agg, float *g_rela,
-                                                            float *g_ar8, int copies, rg_heavy H) {
+                                                            float *g_ar8, int copies, rg_heavy H, int own0) {
     const int lane = threadIdx.x & 31;
     select_copy<D>(g_rela, g_ar8, copies, S.n_table_rows);
     if (H.counters[2]) return;
@@ -946,8 +948,8 @@ __global__ void __launch_bounds__(kBlock) k_edge_bwd_chunks(rg_segments S, const
     for (int c = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); c < n_chunks; c += stride) {
         const int64_t seg = H.chunk_seg[c];
         SegRange r = seg_range<IMPLICIT>(S, seg);
-        const int lo = r.lo + H.chunk_idx[c] * RG_HEAVY_CHUNK_BWD;
-        const int hi = min(r.hi, lo + RG_HEAVY_CHUNK_BWD);
+        const int lo = r.lo + own0 + (H.chunk_idx[c] - 1) * RG_HEAVY_SUB_BWD;   // chunk_idx is 1-based
+        const int hi = min(r.hi, lo + RG_HEAVY_SUB_BWD);
         float4 G[D / 16];
         BwdSmall sm;
         bwd_range<D, HAS_HIDDEN, IMPLICIT>(S, seg, r.q, lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), g_agg,
@@ -1060,6 +1062,7 @@ int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, co
     }
     const size_t tab_bytes = (size_t)seg->n_table_rows * (D + 8) * sizeof(float);
     bool persistent = false;
+    int own0 = RG_HEAVY_CHUNK_BWD;   // slots of a heavy segment its owner warp keeps; the rest: RG_HEAVY_SUB_BWD pieces
     if constexpr (IM) {
         if (pick_variant(seg, D) == 2) {
             auto kern = k_edge_bwd_p<D, HH>;
@@ -1071,8 +1074,10 @@ int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, co
             if (per_sm >= 1) {
                 const int64_t want = rg_cdiv(seg->n_seg, kPWarpsB);
                 const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)n_sm * per_sm);
+                own0 = RG_HEAVY_CHUNK_BWD;
                 kern<<<grid, kPWarpsB * 32, tab_bytes, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,
-                                                            g_hidden, node_small, g_rela, g_ar8, copies, H, has_heavy);
+                                                            g_hidden, node_small, g_rela, g_ar8, copies, H, has_heavy,
+                                                            own0);
                 RG_LAUNCH_CHECK();
                 persistent = true;
             }
@@ -1081,20 +1086,24 @@ int launch_bwd(const rg_segments *seg, const float *hidden, const float *as8, co
     if (!persistent) {
         if (seg->n_seg >= kBlock8MinSegs) {
             const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock * 8);
+            own0 = RG_HEAVY_CHUNK_BWD;
             k_edge_bwd<D, HH, IM, true><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,
                                                                  g_hidden, node_small, g_rela, g_ar8, copies, H,
-                                                                 has_heavy);
+                                                                 has_heavy, own0);
         } else {
             const unsigned grid = (unsigned)rg_cdiv(seg->n_seg, kWarpsPerBlock);
+            // few segments (layer 0 of a training step: one per query): the owner keeps only one small piece, so
+            // that a hub subject does not leave one warp walking hundreds of slots while the GPU idles
+            own0 = seg->n_seg < 4096 ? RG_HEAVY_SUB_BWD : RG_HEAVY_CHUNK_BWD;
             k_edge_bwd<D, HH, IM, false><<<grid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, g_agg,
                                                                   g_hidden, node_small, g_rela, g_ar8, copies, H,
-                                                                  has_heavy);
+                                                                  has_heavy, own0);
         }
         RG_LAUNCH_CHECK();
     }
     if (has_heavy) {
         k_edge_bwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha,
-                                                                    g_agg, g_rela, g_ar8, copies, H);
+                                                                    g_agg, g_rela, g_ar8, copies, H, own0);
         RG_LAUNCH_CHECK();
         k_heavy_fixup<<<kHeavyGrid, kBlock, 0, st>>>(H, D + 24, g_hidden, D, node_small, 24);
         RG_LAUNCH_CHECK();
