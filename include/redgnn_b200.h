@@ -112,7 +112,9 @@ typedef struct rg_segments {
 #define RG_HEAVY_CHUNK 256        /* rg_edge_agg_fwd */
 #endif
 #ifndef RG_HEAVY_CHUNK_BWD
-#define RG_HEAVY_CHUNK_BWD 512    /* rg_edge_agg_bwd: slots a heavy segment's owner warp keeps ...            */
+#define RG_HEAVY_CHUNK_BWD 256    /* rg_edge_agg_bwd: slots a heavy segment's owner warp keeps ...            */
+#endif
+#ifndef RG_HEAVY_SUB_BWD
 #define RG_HEAVY_SUB_BWD 128      /* ... and the size of the pieces the rest is cut into (queue sizing unit) */
 #endif
 typedef struct rg_heavy {
