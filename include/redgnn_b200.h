@@ -109,7 +109,10 @@ typedef struct rg_segments {
  * kernels drain the queue themselves (idle warps take chunks while others still work on segments);
  * the other variants run a second kernel over it. */
 #ifndef RG_HEAVY_CHUNK
-#define RG_HEAVY_CHUNK 256        /* rg_edge_agg_fwd */
+#define RG_HEAVY_CHUNK 256        /* rg_edge_agg_fwd: slots a heavy segment's owner warp keeps ...            */
+#endif
+#ifndef RG_HEAVY_SUB
+#define RG_HEAVY_SUB 256          /* ... and the size of the pieces the rest is cut into (queue sizing unit) */
 #endif
 #ifndef RG_HEAVY_CHUNK_BWD
 #define RG_HEAVY_CHUNK_BWD 256    /* rg_edge_agg_bwd: slots a heavy segment's owner warp keeps ...            */

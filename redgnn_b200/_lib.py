@@ -13,7 +13,7 @@ RG_ABI_VERSION = 1
 RG_COUNTS_WORDS = 8
 RG_CNT_N_IN, RG_CNT_E, RG_CNT_N_OUT, RG_CNT_ERR = 0, 1, 2, 3
 GRAD_COPIES = int(os.environ.get("REDGNN_GRAD_COPIES", "8"))   # relation-gradient accumulator replicas
-RG_HEAVY_CHUNK = int(os.environ.get("REDGNN_HEAVY_CHUNK", "256"))   # must match the library build (developer A/B only)
+RG_HEAVY_CHUNK = int(os.environ.get("REDGNN_HEAVY_SUB", "256"))   # = RG_HEAVY_SUB: queue-sizing unit of the forward (env: A/B builds)
 RG_HEAVY_CHUNK_BWD = int(os.environ.get("REDGNN_HEAVY_SUB_BWD", "128"))   # = RG_HEAVY_SUB_BWD: queue-sizing unit of the backward
 
 

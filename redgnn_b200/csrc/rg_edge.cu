@@ -387,7 +387,7 @@ __device__ __forceinline__ void fwd_block8(const rg_segments &S, int64_t seg0, i
         int hi = __shfl_sync(RG_FULL_MASK, r.hi, src);
         const int64_t sg = seg0 + (src >> 2);
         if (has_heavy && hi - lo > RG_HEAVY_CHUNK) {
-            enqueue_heavy(H, sg, hi - lo, lane);
+            enqueue_heavy(H, sg, hi - lo, lane, RG_HEAVY_SUB, RG_HEAVY_CHUNK);
             hi = lo + RG_HEAVY_CHUNK;
         }
         fwd_range<D, HAS_HIDDEN, IMPLICIT, SMEM_TAB>(S, q, lo, hi, hidden, as8, rela, ar8, aq8, w8, b_alpha, acc,
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kBlock, RG_FWD_MINBLOCKS) k_edge_fwd(rg_segmen
     SegRange r = seg_range<IMPLICIT>(S, seg);
     int hi = r.hi;
     if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {  // without a queue the owner warp does it all
-        enqueue_heavy(H, seg, r.hi - r.lo, lane);
+        enqueue_heavy(H, seg, r.hi - r.lo, lane, RG_HEAVY_SUB, RG_HEAVY_CHUNK);
         hi = r.lo + RG_HEAVY_CHUNK;
     }
     float4 acc[D / 16];
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
                 SegRange r = seg_range<true>(S, seg);
                 q = r.q, lo = r.lo, hi = r.hi;
                 if (has_heavy && r.hi - r.lo > RG_HEAVY_CHUNK) {
-                    enqueue_heavy<true>(H, seg, r.hi - r.lo, lane);
+                    enqueue_heavy<true>(H, seg, r.hi - r.lo, lane, RG_HEAVY_SUB, RG_HEAVY_CHUNK);
                     hi = r.lo + RG_HEAVY_CHUNK;
                 }
                 dst = agg + (size_t)seg * D;
@@ -517,8 +517,8 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
             if (c < 0) break;
             SegRange r = seg_range<true>(S, (int64_t)H.chunk_seg[c]);
             q = r.q;
-            lo = r.lo + H.chunk_idx[c] * RG_HEAVY_CHUNK;
-            hi = min(r.hi, lo + RG_HEAVY_CHUNK);
+            lo = r.lo + RG_HEAVY_CHUNK + (H.chunk_idx[c] - 1) * RG_HEAVY_SUB;   // chunk_idx is 1-based
+            hi = min(r.hi, lo + RG_HEAVY_SUB);
             dst = H.partial + (size_t)c * D;
         }
         float4 acc[D / 16];
@@ -542,8 +542,8 @@ __global__ void __launch_bounds__(kBlock) k_edge_fwd_chunks(rg_segments S, const
     for (int c = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); c < n_chunks; c += stride) {
         const int64_t seg = H.chunk_seg[c];
         SegRange r = seg_range<IMPLICIT>(S, seg);
-        const int lo = r.lo + H.chunk_idx[c] * RG_HEAVY_CHUNK;
-        const int hi = min(r.hi, lo + RG_HEAVY_CHUNK);
+        const int lo = r.lo + RG_HEAVY_CHUNK + (H.chunk_idx[c] - 1) * RG_HEAVY_SUB;
+        const int hi = min(r.hi, lo + RG_HEAVY_SUB);
         float4 acc[D / 16];
         fwd_range<D, HAS_HIDDEN, IMPLICIT>(S, r.q, lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), acc);
         store_row<D>(H.partial + (size_t)c * D, acc, lane);
