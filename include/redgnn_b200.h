@@ -308,6 +308,13 @@ int rg_node_wgrad(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_de
 int rg_attn_tables(int32_t hidden_dim, int32_t attn_dim, int32_t n_rows, int32_t n_query, const float *rela,
                    const float *Wr, const float *Wqr, const float *bqr, const float *w_alpha,
                    const int64_t *q_rel, float *ar8, float *aq8, float *w8, void *stream);
+/* Fused training loss on the per-node scores (base_model.py:58-60) without the dense (n, n_ent) matrix:
+ *   loss_q[q] = -scores_all[q][obj[q]] + logsumexp_e scores_all[q][e]
+ * with the visited nodes of query q = rows [qinfo[q].base, +count) of `score` / `node_e` and every
+ * unvisited entity scoring exactly 0 (models.py:87-88).  Also writes d loss_q / d score as rows
+ * {g, 0 x 7} of g_small [N][8] (the upstream operand of rg_node_bwd for the last layer). */
+int rg_node_loss(int32_t n_query, int32_t n_ent, const float *score, const int32_t *node_e,
+                 const int32_t *qinfo, const int64_t *obj, float *loss_q, float *g_small, void *stream);
 int rg_attn_param_grads(int32_t hidden_dim, int32_t attn_dim, int32_t n_rows, int32_t n_query,
                         int32_t grad_copies, const float *rela, const float *Wr, const float *Wqr,
                         const int64_t *q_rel, const float *g_rela_copies, const float *g_ar8_copies,

@@ -179,3 +179,66 @@ extern "C" int rg_attn_param_grads(int32_t hidden_dim, int32_t attn_dim, int32_t
     RG_LAUNCH_CHECK();
     return RG_OK;
 }
+
+// ---- fused training loss on the per-node scores (reference Static/transductive/base_model.py:58-60) ------
+//   loss_q = -scores_all[q][obj_q] + logsumexp_e scores_all[q][e]
+// evaluated WITHOUT materialising the dense (n, n_ent) score matrix: the visited nodes of query q are the
+// rows [base, base + count) of `score`, every unvisited entity scores exactly 0 (models.py:87-88), so
+//   logsumexp = m + log( sum_visited exp(s - m) + (n_ent - count) exp(-m) ),  m = max(max_visited s, 0 if any unvisited)
+// and the positive is the visited row whose entity is obj_q (0 if unvisited).  Also writes the gradient
+//   g_score[row] = softmax probability - [entity == obj_q]
+// as rows {g, 0 x 7} of the g_small operand of rg_node_bwd (stride 8).  One CTA per query; fixed order.
+namespace {
+constexpr int kLossThreads = 256;
+__device__ __forceinline__ float block_reduce(float v, float *sm, bool is_max) {
+    for (int o = 16; o > 0; o >>= 1) {
+        const float t = __shfl_xor_sync(RG_FULL_MASK, v, o);
+        v = is_max ? fmaxf(v, t) : v + t;
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = sm[0];
+    for (int i = 1; i < kLossThreads / 32; ++i) r = is_max ? fmaxf(r, sm[i]) : r + sm[i];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kLossThreads) k_node_loss(const float *__restrict__ score,
+                                                            const int32_t *__restrict__ node_e,
+                                                            const int32_t *__restrict__ qinfo,
+                                                            const int64_t *__restrict__ obj, int n_ent,
+                                                            float *__restrict__ loss_q, float *__restrict__ g_small) {
+    __shared__ float sm[kLossThreads / 32];
+    __shared__ float s_pos;
+    const int q = blockIdx.x, base = qinfo[2 * q], cnt = qinfo[2 * q + 1];
+    const int target = (int)obj[q];
+    if (threadIdx.x == 0) s_pos = 0.f;
+    float mx = cnt < n_ent ? 0.f : -INFINITY;
+    for (int i = threadIdx.x; i < cnt; i += kLossThreads) mx = fmaxf(mx, __ldg(score + base + i));
+    mx = block_reduce(mx, sm, true);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < cnt; i += kLossThreads) {
+        const float v = __ldg(score + base + i);
+        s += __expf(v - mx);
+        if (__ldg(node_e + base + i) == target) s_pos = v;   // at most one row per query holds the target
+    }
+    s = block_reduce(s, sm, false) + (float)(n_ent - cnt) * __expf(-mx);
+    if (threadIdx.x == 0) loss_q[q] = -s_pos + mx + __logf(s);
+    const float inv = 1.f / s;
+    for (int i = threadIdx.x; i < cnt; i += kLossThreads) {
+        const float p = __expf(__ldg(score + base + i) - mx) * inv;
+        const float g = p - (__ldg(node_e + base + i) == target ? 1.f : 0.f);
+        float4 *o = reinterpret_cast<float4 *>(g_small + (size_t)(base + i) * 8);
+        o[0] = make_float4(g, 0.f, 0.f, 0.f);
+        o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+}  // namespace
+
+extern "C" int rg_node_loss(int32_t n_query, int32_t n_ent, const float *score, const int32_t *node_e,
+                            const int32_t *qinfo, const int64_t *obj, float *loss_q, float *g_small, void *stream) {
+    if (n_query <= 0 || n_ent <= 0 || !score || !node_e || !qinfo || !obj || !loss_q || !g_small) return RG_ERR_BAD_ARG;
+    k_node_loss<<<n_query, kLossThreads, 0, (cudaStream_t)stream>>>(score, node_e, qinfo, obj, n_ent, loss_q, g_small);
+    RG_LAUNCH_CHECK();
+    return RG_OK;
+}

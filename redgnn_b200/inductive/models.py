@@ -9,3 +9,7 @@ class RED_GNN_induc(RedGNN):
         """models.py:65-89: 'transductive' -> training graph / n_ent, else unseen-entity graph / n_ent_ind."""
         graph = self.loader.graph_for(mode, self.W_final.weight.device)
         return self._run(subs, rels, graph, self.loader.n_ent_for(mode))
+
+    def _graph_and_width(self, mode):
+        mode = 'transductive' if mode is None else mode
+        return self.loader.graph_for(mode, self.W_final.weight.device), self.loader.n_ent_for(mode)

@@ -186,8 +186,8 @@ class RedGNN(torch.nn.Module):
     grads_in_place = False             # see train_graph.TrainStepFunction
     MAX_CACHED_TRAIN_GRAPHS = 2
 
-    def _run_train_graph(self, q_sub, q_rel, graph, n_ent_out):
-        from .train_graph import TrainStepRunner, TrainStepFunction
+    def _run_train_graph(self, q_sub, q_rel, graph, n_ent_out, objs=None):
+        from .train_graph import TrainStepRunner, TrainStepFunction, TrainLossFunction
         p_drop = float(self.dropout.p) if self.training else 0.0
         key = (q_sub.shape[0], id(graph), graph.epoch, n_ent_out, p_drop,
                tuple(p.data_ptr() for p in self.parameters()))
@@ -204,10 +204,40 @@ class RedGNN(torch.nn.Module):
             finally:
                 self.dropout.p = saved_p
             cache[key] = runner
-        scores = TrainStepFunction.apply(runner, q_sub, q_rel, *[runner.params[k] for k in runner.names])
+        params = [runner.params[k] for k in runner.names]
+        if objs is not None:
+            out = TrainLossFunction.apply(runner, q_sub, q_rel, objs, *params)
+        else:
+            out = TrainStepFunction.apply(runner, q_sub, q_rel, *params)
         self._last_stats = runner.frontiers
         self._last_runner = runner
-        return scores
+        return out
+
+    def loss(self, subs, rels, objs, mode=None):
+        """The training loss of base_model.py:58-60,
+            sum_q ( -scores[q, objs[q]] + logsumexp_e scores[q, e] ),   scores = self.forward(subs, rels, mode),
+        WITHOUT the dense (n, n_ent) score matrix when the graph-captured training step is available
+        (train() mode, hidden_dim <= 48): rg_node_loss evaluates it on the per-node scores (unvisited entities
+        score exactly 0) and its gradient feeds the node backward directly.  Otherwise the dense formula."""
+        dev = self.W_final.weight.device
+        n, d = len(subs), self.hidden_dim
+        graph, n_ent_out = self._graph_and_width(mode)
+        ok = (torch.is_grad_enabled() and self.training and self.graph_train and d <= 48 and n > 0 and dev.type == 'cuda'
+              and _lib.Stats.timing is None and n * graph.n_ent * d * 4 * 9 * self.n_layer <= self.ASYNC_BUDGET_BYTES)
+        objs_t = self._to_device(objs, dev)
+        if ok:
+            with torch.cuda.device(dev):
+                self._last_runner = None
+                q_sub, q_rel = self._to_device(subs, dev), self._to_device(rels, dev)
+                if not isinstance(subs, torch.Tensor):
+                    s_np = np.asarray(subs)
+                    if s_np.min() < 0 or s_np.max() >= graph.n_ent:
+                        raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % graph.n_ent)
+                return self._run_train_graph(q_sub, q_rel, graph, n_ent_out, objs=objs_t)
+        scores = self.forward(subs, rels) if mode is None else self.forward(subs, rels, mode)
+        pos = scores[torch.arange(n, device=dev), objs_t]
+        mx = scores.max(1, keepdim=True)[0]
+        return torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(scores - mx), 1)))
 
     def flat_grad(self):
         """With `grads_in_place`: the flat gradient buffer of the latest graph-captured training step

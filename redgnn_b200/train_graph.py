@@ -75,6 +75,7 @@ class TrainStepRunner(object):
         self.scores = None
         self.version = 0
         self.bwd_graphs = {}           # one entry: (CUDAGraph, launches)
+        self.bwd_loss_graph, self.g_small_loss, self.loss_q = None, None, None   # fused-loss variant (lazy)
         self.bwd_replays = 0
         self._build()
 
@@ -140,7 +141,7 @@ class TrainStepRunner(object):
         return scores
 
     # ------------------------------------------------------------------------------------------
-    def _backward(self, caps=None):
+    def _backward(self, caps=None, from_loss=False):
         """Hand-written backward of the whole path on the buffers of the last forward replay.  Every
         kernel stops at the device-side node counts, so nothing here depends on the true sizes
         (`caps` is accepted for compatibility and ignored): ONE captured variant, no host read-back,
@@ -156,11 +157,15 @@ class TrainStepRunner(object):
         gv = self.grad_views
         self.flat_grad.zero_()                                   # the GRU gradients accumulate over the layers
         last = self.L[-1]
-        # upstream of the last layer: g_hidden = g_score * W_final, expressed as g_small . w_small (1 row)
-        g_small = e(cap, 8)
-        check(lib.rg_gather_scores(cap, ptr(last["n_dev"]), ptr(last["nb"]), ptr(last["ne"]), ptr(self.g_out),
-                                   self.n_ent_out, ptr(g_small), 8, st()))
-        _lib.Stats.launches += 1
+        # upstream of the last layer: g_hidden = g_score * W_final, expressed as g_small . w_small (1 row);
+        # g_score comes from the dense score gradient (gather) or straight from the fused loss kernel
+        if from_loss:
+            g_small = self.g_small_loss
+        else:
+            g_small = e(cap, 8)
+            check(lib.rg_gather_scores(cap, ptr(last["n_dev"]), ptr(last["nb"]), ptr(last["ne"]), ptr(self.g_out),
+                                       self.n_ent_out, ptr(g_small), 8, st()))
+            _lib.Stats.launches += 1
         g_small_stride, w_small, w_rows, ws_dst = 8, m.W_final.weight, 1, gv["W_final.weight"]
         g_hid_e, g_h0_next, remap = None, None, None
         gate = m.gate
@@ -248,14 +253,38 @@ class TrainStepRunner(object):
             raise _lib.RgError("query subject out of range for this graph (n_ent=%d)" % self.graph.n_ent)
         return [int(x) for x in c[:-1]]
 
-    def _capture_backward(self, caps, warm=True):
+    def _capture_backward(self, caps, warm=True, from_loss=False):
         g = torch.cuda.CUDAGraph()
         before = _lib.Stats.launches
         with torch.no_grad(), torch.cuda.graph(g, pool=self.fwd_graph.pool()):
-            self._backward()
+            self._backward(from_loss=from_loss)
         launches = _lib.Stats.launches - before
         _lib.Stats.launches = before
-        self.bwd_graphs[caps] = (g, launches)
+        if from_loss:
+            self.bwd_loss_graph = (g, launches)
+        else:
+            self.bwd_graphs[caps] = (g, launches)
+
+    # ---- fused loss (base_model.py:58-60) on the per-node scores: no dense (n, n_ent) round trip ----------
+    def fused_loss(self, objs):
+        """After a forward replay: per-query losses [n] and, as a side effect, d loss / d score in
+        `g_small_loss` (the upstream operand of the last layer's rg_node_bwd)."""
+        if self.g_small_loss is None:
+            self.g_small_loss = torch.zeros((self.cap, 8), dtype=torch.float32, device=self.dev)
+            self.loss_q = torch.zeros(self.n, dtype=torch.float32, device=self.dev)
+        last = self.L[-1]
+        check(lib.rg_node_loss(self.n, self.n_ent_out, ptr(self.score_node), ptr(last["ne"]), ptr(last["fr_out"].qinfo),
+                               ptr(objs), ptr(self.loss_q), ptr(self.g_small_loss), stream_ptr()))
+        _lib.Stats.launches += 1
+        return self.loss_q
+
+    def replay_backward_from_loss(self):
+        if self.bwd_loss_graph is None:
+            self._capture_backward(None, from_loss=True)
+        g, launches = self.bwd_loss_graph
+        g.replay()
+        _lib.Stats.launches += launches
+        self.bwd_replays += 1
 
     def replay_backward(self):
         """One captured backward (all kernels read the true node counts on the device): no host
@@ -308,3 +337,41 @@ class TrainStepFunction(torch.autograd.Function):
             out.append(flat[off:off + p.numel()].view_as(p))
             off += p.numel()
         return (None, None, None) + tuple(out)
+
+
+class TrainLossFunction(torch.autograd.Function):
+    """loss = sum_q ( -score[q, obj_q] + logsumexp_e score[q, e] )  (base_model.py:58-60) of a graph-captured
+    training forward, computed on the per-node scores by rg_node_loss: the dense (n, n_ent) score matrix
+    is neither read nor differentiated through."""
+
+    @staticmethod
+    def forward(ctx, runner, q_sub, q_rel, objs, *params):
+        runner.sub.copy_(q_sub)
+        runner.rel.copy_(q_rel)
+        runner.fwd_graph.replay()
+        _lib.Stats.launches += runner.fwd_launches
+        runner.version += 1
+        ctx.runner, ctx.version = runner, runner.version
+        ctx.in_place = bool(getattr(runner.model, "grads_in_place", False))
+        if ctx.in_place:
+            for k in runner.names:
+                runner.params[k].grad = runner.grad_views[k]
+        return runner.fused_loss(objs).sum()
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        r = ctx.runner
+        if ctx.version != r.version:
+            raise _lib.RgError("redgnn_b200: a graph-captured training forward was followed by another forward of "
+                               "the same batch size before its backward")
+        r.g_small_loss.mul_(g_loss)                    # d loss / d score, scaled by the upstream gradient (usually 1)
+        r.replay_backward_from_loss()
+        if ctx.in_place:
+            return (None, None, None, None) + (None,) * len(r.names)
+        flat = r.flat_grad.clone()
+        out, off = [], 0
+        for k in r.names:
+            p = r.params[k]
+            out.append(flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        return (None, None, None, None) + tuple(out)

@@ -493,3 +493,43 @@ def cuda_loss_backward_train(model, tri):
     loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1)))
     loss.backward()
     return loss
+
+
+@pytest.mark.parametrize("fixture,n_layer", [("tiny_dir", 3), ("hub_dir", 2)])
+def test_fused_loss_matches_dense_loss_and_gradients(request, fixture, n_layer):
+    """model.loss(subs, rels, objs) (rg_node_loss on the per-node scores, no dense (n, n_ent) matrix) against
+    the reference's dense formula (base_model.py:58-60) on model.forward's scores: value and every gradient;
+    includes queries whose target entity is NOT visited (its score is the implicit 0)."""
+    from redgnn_b200 import TransductiveLoader, RED_GNN_trans
+    L = TransductiveLoader(request.getfixturevalue(fixture))
+    model = RED_GNN_trans(Options(hidden_dim=48, attn_dim=5, n_layer=n_layer, dropout=0.0, act="relu", n_rel=L.n_rel), L).cuda()
+    model.train()
+    tri = L.get_batch(np.arange(14)).copy()
+    with torch.no_grad():
+        sc = model(tri[:, 0], tri[:, 1])
+    unvisited = (sc[0] == 0).nonzero().flatten()
+    if len(unvisited):
+        tri[0, 2] = int(unvisited[0])                       # a target outside the query's subgraph
+    res = {}
+    for fused in (False, True):
+        model.zero_grad(set_to_none=True)
+        if fused:
+            loss = model.loss(tri[:, 0], tri[:, 1], tri[:, 2])
+        else:
+            out = model(tri[:, 0], tri[:, 1])
+            pos = out[torch.arange(len(out)).cuda(), torch.as_tensor(tri[:, 2]).cuda()]
+            mx = out.max(1, keepdim=True)[0]
+            loss = torch.sum(-pos + mx.squeeze(1) + torch.log(torch.sum(torch.exp(out - mx), 1)))
+        loss.backward()
+        res[fused] = (loss.detach().clone(), {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    assert_close(res[True][0], res[False][0], 1e-5, "fused loss value")
+    floor = 1e-7 * max(float(g.abs().max()) for g in res[False][1].values())
+    for k in res[False][1]:
+        a, b = res[True][1][k], res[False][1][k]
+        err = float((a - b).abs().max())
+        assert err <= 2e-4 * float(b.abs().max()) or err <= floor, "fused-loss grad %s: err %.3e" % (k, err)
+    # scaled upstream gradient
+    model.zero_grad(set_to_none=True)
+    (0.5 * model.loss(tri[:, 0], tri[:, 1], tri[:, 2])).backward()
+    for k, p in model.named_parameters():
+        assert_close(p.grad, 0.5 * res[True][1][k], 1e-5, "scaled " + k)
