@@ -131,36 +131,41 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
     return v;
 }
 
-// Persistent kernels drain the heavy-chunk queue THEMSELVES: a warp that has run out of segments
-// takes chunks (counters[3]) as soon as their entries are published, until every warp of the grid
-// has finished producing (counters[4] == total_warps) and the queue is empty.  All CTAs of a
-// persistent launch are co-resident (grid <= occupancy x SMs), so the polling cannot deadlock.  The
-// chunk work thereby overlaps the tail of the segment work instead of running as a second,
-// latency-bound kernel behind it.  Returns the chunk to process or -1.  Warp-collective.
+// The persistent forward drains the heavy-chunk queue ITSELF: a warp that has run out of segments takes
+// chunks (counters[3]) as soon as their entries are published, until every warp of the grid has finished
+// producing (counters[4] == total_warps) and the queue is empty.  The chunk work thereby overlaps the tail
+// of the segment work instead of running as a second, latency-bound kernel behind it.
+// The drain is OPPORTUNISTIC, never required for correctness: a finished chunk is marked by negating its
+// chunk_idx, and k_edge_fwd_chunks runs after the kernel over whatever is still positive (normally nothing:
+// a few microseconds).  A warp therefore never waits unboundedly -- if the CTAs of this launch are not all
+// co-resident (another stream or process holding SMs), producers it would wait for may not be running;
+// after kDrainPolls fruitless polls it simply leaves.  Returns the chunk to process or -1.  Warp-collective.
+constexpr int kDrainPolls = 512;   // x up to ~4 us of back-off each: ~2 ms of fruitless waiting at most
 __device__ __forceinline__ int heavy_take(const rg_heavy &H, int total_warps, int lane) {
-    int c = 0;
+    int c = -1;
     if (lane == 0) {
-        c = atomicAdd(&H.counters[3], 1);
-        unsigned backoff = 256;   // ns; doubles up to ~8 us: thousands of idle warps must not hammer the L2
-                                  // lines of the counters while the working warps stream their atomics
-        for (;;) {
-            if (ld_acquire(&H.counters[2])) { c = -1; break; }   // queue overflow (reported to the caller)
+        // claim the next index once (one atomic per take: a compare-and-swap that never overshoots was measured
+        // -- thousands of idle warps retrying it serialise on one L2 line, 8.5 -> 400 ms per step)
+        const int t = atomicAdd(&H.counters[3], 1);
+        unsigned backoff = 256;   // ns; doubles up to ~4 us: idle warps must not hammer the counters' L2 lines
+        for (int polls = 0; polls < kDrainPolls; ++polls) {
+            if (ld_acquire(&H.counters[2])) break;               // queue overflow (reported to the caller)
             int reserved = min(ld_acquire(&H.counters[0]), H.max_chunks);
-            if (c < reserved) {
-                while (ld_acquire(&H.chunk_idx[c]) == 0) {
-                    if (ld_acquire(&H.counters[2])) { c = -1; break; }
-                    __nanosleep(128);
-                }
+            if (t < reserved) {                                   // exists; its entry is published at once or very soon
+                int spins = 0;
+                while (ld_acquire(&H.chunk_idx[t]) == 0 && ++spins < 4096) __nanosleep(64);
+                if (spins < 4096) c = t;
                 break;
             }
-            if (ld_acquire(&H.counters[4]) >= total_warps) {     // no producer left: final look at the queue
+            if (ld_acquire(&H.counters[4]) >= total_warps) {      // no producer left: final look at the queue
                 reserved = min(ld_acquire(&H.counters[0]), H.max_chunks);
-                if (c >= reserved) { c = -1; break; }
+                if (t >= reserved) break;
                 continue;
             }
             __nanosleep(backoff);
-            if (backoff < 8192) backoff <<= 1;
+            if (backoff < 4096) backoff <<= 1;
         }
+        // (giving up leaves index t -- should a producer still create it -- to the clean-up kernel)
     }
     return __shfl_sync(RG_FULL_MASK, c, 0);
 }
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
     int64_t seg = (int64_t)blockIdx.x * kPWarps + (threadIdx.x >> 5);
     const int64_t stride = (int64_t)gridDim.x * kPWarps;
     bool draining = false;
+    int done_c = 0;
     for (;;) {
         int q, lo, hi;
         float *dst;
@@ -515,6 +521,7 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
         } else {
             const int c = heavy_take(H, (int)stride, lane);
             if (c < 0) break;
+            done_c = c;
             SegRange r = seg_range<true>(S, (int64_t)H.chunk_seg[c]);
             q = r.q;
             lo = r.lo + RG_HEAVY_CHUNK + (H.chunk_idx[c] - 1) * RG_HEAVY_SUB;   // chunk_idx is 1-based
@@ -524,6 +531,7 @@ __global__ void __launch_bounds__(kPWarps * 32, 2) k_edge_fwd_p(rg_segments S, c
         float4 acc[D / 16];
         fwd_range<D, HAS_HIDDEN, true, true>(S, q, lo, hi, hidden, as8, rela, ar8, aq8, w8, ba, acc, s_rela, s_ar8);
         store_row<D>(dst, acc, lane);
+        if (draining && lane == 0) H.chunk_idx[done_c] = -H.chunk_idx[done_c];   // finished: the clean-up kernel skips it
     }
 }
 
@@ -540,9 +548,11 @@ __global__ void __launch_bounds__(kBlock) k_edge_fwd_chunks(rg_segments S, const
     const int n_chunks = min(H.counters[0], H.max_chunks);
     const int stride = gridDim.x * kWarpsPerBlock;
     for (int c = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); c < n_chunks; c += stride) {
+        const int idx = H.chunk_idx[c];
+        if (idx <= 0) continue;   // already reduced by the persistent kernel's own drain (warp-uniform)
         const int64_t seg = H.chunk_seg[c];
         SegRange r = seg_range<IMPLICIT>(S, seg);
-        const int lo = r.lo + RG_HEAVY_CHUNK + (H.chunk_idx[c] - 1) * RG_HEAVY_SUB;
+        const int lo = r.lo + RG_HEAVY_CHUNK + (idx - 1) * RG_HEAVY_SUB;
         const int hi = min(r.hi, lo + RG_HEAVY_SUB);
         float4 acc[D / 16];
         fwd_range<D, HAS_HIDDEN, IMPLICIT>(S, r.q, lo, hi, hidden, as8, rela, ar8, aq8, w8, __ldg(b_alpha), acc);
@@ -1038,10 +1048,9 @@ int launch_fwd(const rg_segments *seg, const float *hidden, const float *as8, co
         RG_LAUNCH_CHECK();
     }
     if (has_heavy) {
-        if (!persistent) {   // the persistent kernel has drained the queue itself
-            k_edge_fwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, H);
-            RG_LAUNCH_CHECK();
-        }
+        // all chunks (non-persistent main kernel) or whatever the persistent kernel's own drain left positive
+        k_edge_fwd_chunks<D, HH, IM><<<kHeavyGrid, kBlock, 0, st>>>(*seg, hidden, as8, rela, ar8, aq8, w8, b_alpha, H);
+        RG_LAUNCH_CHECK();
         k_heavy_fixup<<<kHeavyGrid, kBlock, 0, st>>>(H, D, agg, D, nullptr, 0);
         RG_LAUNCH_CHECK();
     }
