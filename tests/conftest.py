@@ -13,6 +13,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: full-size shape, tens of seconds on the GPU box")
 
 
+def pytest_terminal_summary(terminalreporter):
+    """Gradient parity: how many tensors were accepted by which branch of helpers.assert_grad_close
+    (1e-4 against the fp64 oracle / within 4x the reference's own fp32 error / below the absolute floor)."""
+    try:
+        import helpers
+    except Exception:
+        return
+    if sum(helpers.GRAD_BRANCHES.values()):
+        terminalreporter.write_line("gradient parity branches: %s" % helpers.GRAD_BRANCHES)
+
+
 @pytest.fixture(scope="session")
 def tiny_dir(tmp_path_factory):
     from redgnn_b200 import synth

@@ -93,6 +93,9 @@ def grad_floor(grads64):
     return 1e-7 * max(float(g.abs().max()) for g in grads64.values())
 
 
+GRAD_BRANCHES = {"rtol": 0, "fp32-yardstick": 0, "floor": 0}      # how often each acceptance branch fired (conftest prints it)
+
+
 def assert_grad_close(mine, ref32, ref64, rtol=1e-4, tag="", floor=0.0):
     """Gradient parity.  Pass if max|mine - ref64| <= rtol * max|ref64|, or -- for sums with heavy
     cancellation, where fp32 itself cannot hold rtol -- if the error is within 4x the error the
@@ -102,6 +105,9 @@ def assert_grad_close(mine, ref32, ref64, rtol=1e-4, tag="", floor=0.0):
     assert m.shape == r64.shape, "%s shape %s vs %s" % (tag, tuple(m.shape), tuple(r64.shape))
     scale = r64.abs().max().clamp_min(1e-30)
     err, err_ref = (m - r64).abs().max(), (r32 - r64).abs().max()
+    branch = "rtol" if err <= rtol * scale else ("fp32-yardstick" if err <= 4 * err_ref else ("floor" if err <= floor else None))
+    if branch:
+        GRAD_BRANCHES[branch] += 1
     assert err <= rtol * scale or err <= 4 * err_ref or err <= floor, \
         "%s: max abs err %.3e (fp32 reference itself: %.3e) vs scale %.3e (rel %.3e > %.1e)" % (
             tag, err.item(), err_ref.item(), scale.item(), (err / scale).item(), rtol)
