@@ -94,3 +94,52 @@ def test_two_rank_train_step_matches_single_process():
     assert float(np.abs(res[0][3]).max()) == 0.0          # grad-less parameter: explicit zeros on every rank
     for r in res:
         assert np.allclose(r[4][:3], ref_stats[:3]) and r[4][3] == 25
+
+
+class FlatToy(Toy):
+    """Toy whose gradients live in ONE flat buffer (what RedGNN.flat_grad() provides with
+    `grads_in_place`): every p.grad is a view of it, so the exchange is a single in-place all-reduce."""
+
+    def __init__(self):
+        super().__init__()
+        n = sum(p.numel() for p in self.parameters())
+        self._flat = torch.zeros(n)
+        off = 0
+        for p in self.parameters():
+            p.grad = self._flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def flat_grad(self):
+        return self._flat
+
+
+def _flat_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = FlatToy()
+        with torch.no_grad():
+            for p in model.parameters():
+                p.grad.fill_(float(rank + 1))            # "local" gradients, written in place
+        n = rgd.allreduce_model_gradients(model)
+        q.put((rank, n, [float(p.grad.flatten()[0]) for p in model.parameters()],
+               all(p.grad.data_ptr() >= model._flat.data_ptr() for p in model.parameters())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_in_place_gradient_allreduce_two_ranks():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n_param = sum(p.numel() for p in Toy().parameters())
+    for rank, n, firsts, still_views in res:
+        assert n == n_param and still_views
+        assert all(abs(v - 3.0) < 1e-6 for v in firsts)       # 1 + 2 summed, identical on both ranks
