@@ -252,10 +252,14 @@ int rg_node_update(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_d
 
 /* Training forward of the same node update (tensor-core kernel, hidden_dim <= 48): applies the
  * caller's dropout mask (models.py:82; values 0 or 1/(1-p), NULL = no dropout) between act(W_h agg)
- * and the GRU and writes saved[6][n][D] = {act(W_h agg), r, z, n, W_hn h0 + b_hn, h0} for the
- * backward pass.  rg_gru_bwd_elem is the elementwise part of that backward:
- *   g_gi[n][3D], g_gh[n][3D] = gradients of the GRU pre-activations (r, z, n) on the input / hidden
- *   side, g_h0_direct[n][D] = g_hidden * z; the GEMMs around it are plain library calls. */
+ * and the GRU and writes six planes saved[6] = {act(W_h agg), r, z, n, W_hn h0 + b_hn, h0} for the
+ * backward pass (rg_node_bwd / rg_node_wgrad).  Each plane is LANE-INTERLEAVED: 32-row tiles, inside a
+ * tile [chunk = col / 4][row % 32][4 floats] + 4 pad floats per chunk, i.e. element (row, col) sits at
+ *   ((row / 32) * (D / 4) + col / 4) * 132 + (row % 32) * 4 + col % 4      (floats)
+ * and a plane of n rows holds ceil(n / 32) * (D / 4) * 132 floats (csrc/rg_tc.cuh; coalesced for the
+ * tensor-core kernels, whose lanes are node rows).  G4 (four planes) and g_pre of rg_node_bwd use the same
+ * layout.  Optionally also emits the NEXT layer's attention projection as8 = Ws_next[ws_rows][D] . hidden
+ * and / or the scores W_final . hidden. */
 int rg_node_update_train(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev,
                          const float *agg, const float *h_prev,
                          const int32_t *src, const float *W_h, const float *W_ih, const float *W_hh,
@@ -320,26 +324,15 @@ int rg_attn_param_grads(int32_t hidden_dim, int32_t attn_dim, int32_t n_rows, in
                         const int64_t *q_rel, const float *g_rela_copies, const float *g_ar8_copies,
                         const float *q_part, int32_t q_slices, float *g_rela, float *g_Wr, float *g_Wqr,
                         float *g_bqr, float *g_w_alpha, float *g_b_alpha, void *stream);
-/* saved_plane_rows: rows per plane of `saved` (0 = n_nodes); lets a caller process only the first
- * n_nodes <= saved_plane_rows rows of buffers that were written with a larger row capacity. */
-int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_rows, const int64_t *n_nodes_dev,
-                    const float *g_hidden, const float *saved, float *g_gi, float *g_gh, float *g_h0_direct,
-                    float *bias_partial /* optional [ceil(n/64)][4][D]: per-CTA column sums of g_r, g_z, g_n, g_n*r */,
-                    void *stream);
-
 /* Glue of the graph-captured training step (all shape-static, true counts read on the device):
  *   rg_gather_scores: backward of rg_scatter_scores, g_node[j * out_stride] = g_scores_all[b_j][e_j] (0 past n);
  *                     out_stride 8 writes whole rows {g, 0 x 7} = the g_small operand of rg_node_bwd;
- *   rg_scatter_rows : dst[src[j]] (+)= rows[j] for src[j] >= 0 -- gradient of the h0 re-index
- *                     (models.py:81), src = the inverse map of rg_frontier_remap;
  *   rg_query_sum8   : partial[q][32][0..23] = slice sums of rows24[.][0..23] over the node rows of query q
  *                     (rg_frontier.qinfo ranges); adding the 32 slices gives, in a fixed order, the
  *                     per-query attention-bias gradient (cols 0..7) and the w_alpha / b_alpha sums. */
 int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *node_b,
                      const int32_t *node_e, const float *g_scores_all, int32_t n_ent_out, float *g_node,
                      int32_t out_stride, void *stream);
-int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *src,
-                    const float *rows, float *dst, int32_t accumulate, void *stream);
 int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *partial, void *stream);
 
 /* Filtered ranking on the device: utils.cal_ranks (transductive/utils.py:7-14: rankdata 'average'

@@ -77,9 +77,7 @@ SIGNATURES = {
     "rg_node_loss": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 7),
     "rg_attn_tables": (C.c_int, [C.c_int32] * 4 + [C.c_void_p] * 10),
     "rg_attn_param_grads": (C.c_int, [C.c_int32] * 5 + [C.c_void_p] * 7 + [C.c_int32] + [C.c_void_p] * 7),
-    "rg_gru_bwd_elem": (C.c_int, [C.c_int32, C.c_int64, C.c_int64] + [C.c_void_p] * 8),
     "rg_gather_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
-    "rg_scatter_rows": (C.c_int, [C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
     "rg_query_sum8": (C.c_int, [C.c_int32] + [C.c_void_p] * 4),
     "rg_filtered_ranks": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 7),
     "rg_scatter_scores": (C.c_int, [C.c_int64] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p, C.c_void_p]),

@@ -270,26 +270,6 @@ __global__ void __launch_bounds__(256) k_gather_scores(int64_t n_host, const int
     }
 }
 
-// dst[src[j]] = rows[j] for j < n with src[j] >= 0 (src injective): gradient of the h0 re-index
-__global__ void __launch_bounds__(256) k_scatter_rows(int64_t n_host, const int64_t *__restrict__ n_dev, int D4,
-                                                      const int32_t *__restrict__ src,
-                                                      const float4 *__restrict__ rows, float4 *__restrict__ dst,
-                                                      int accumulate) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    const int64_t n = n_dev ? *n_dev : n_host;
-    const int64_t j = i / D4;
-    if (j >= n) return;
-    const int s = src[j];
-    if (s < 0) return;
-    float4 *o = dst + (size_t)s * D4 + (i % D4);
-    float4 v = rows[i];
-    if (accumulate) {  // src is injective: no two threads touch the same destination
-        const float4 c = *o;
-        v = make_float4(v.x + c.x, v.y + c.y, v.z + c.z, v.w + c.w);
-    }
-    *o = v;
-}
-
 // partial[q][slice][0..23] = sum over the slice's share of the query's node rows [base, base+count)
 // of rows24[.][0..23]; the caller adds the kQuerySlices partials (fixed order => deterministic)
 constexpr int kQuerySlices = 32;
@@ -324,18 +304,6 @@ extern "C" int rg_gather_scores(int64_t n_nodes, const int64_t *n_nodes_dev, con
     return RG_OK;
 }
 
-extern "C" int rg_scatter_rows(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_nodes_dev, const int32_t *src,
-                               const float *rows, float *dst, int32_t accumulate, void *stream) {
-    if (n_nodes < 0 || hidden_dim <= 0 || hidden_dim % 4 || !src || !rows || !dst) return RG_ERR_BAD_ARG;
-    if (n_nodes == 0) return RG_OK;
-    const int d4 = hidden_dim / 4;
-    k_scatter_rows<<<(unsigned)rg_cdiv(n_nodes * d4, 256), 256, 0, (cudaStream_t)stream>>>(
-        n_nodes, n_nodes_dev, d4, src, reinterpret_cast<const float4 *>(rows), reinterpret_cast<float4 *>(dst),
-        accumulate);
-    RG_LAUNCH_CHECK();
-    return RG_OK;
-}
-
 extern "C" int rg_query_sum8(int32_t n_query, const float *rows24, const int32_t *qinfo, float *partial,
                              void *stream) {
     if (n_query <= 0 || !rows24 || !qinfo || !partial) return RG_ERR_BAD_ARG;
@@ -361,87 +329,6 @@ int rg_node_update_tc(int32_t hidden_dim, int64_t n_nodes, const int64_t *n_node
                       const float *W_hh, const float *b_ih, const float *b_hh, const float *Ws_next,
                       const float *W_final, int32_t act, float *hidden, float *as8, float *score,
                       const float *drop_mask, float *saved, int32_t ws_rows, cudaStream_t st);
-
-// elementwise part of the GRU-cell backward (the GEMMs around it are plain library calls).
-// One CTA = kGruRows consecutive nodes x all D columns (thread = (row lane, column)); besides the
-// per-element gradients it writes the CTA's column sums of {g_r, g_z, g_n, g_n * r} to
-// bias_partial[blockIdx][4][D] (optional) -- the bias gradients are then a tiny fixed-order sum over
-// CTAs instead of two full-matrix reductions.
-constexpr int kGruRows = 64;
-
-template <int D>
-__global__ void __launch_bounds__(4 * D) k_gru_bwd_elem(int64_t n_rows, int64_t plane_rows,
-                                                        const int64_t *__restrict__ n_dev,
-                                                        const float *__restrict__ g_h,
-                                                        const float *__restrict__ saved, float *__restrict__ g_gi,
-                                                        float *__restrict__ g_gh, float *__restrict__ g_h0d,
-                                                        float *__restrict__ bias_partial) {
-    __shared__ float sm[4][4][D];
-    const int c = threadIdx.x % D, rl = threadIdx.x / D;  // 4 row lanes
-    const int64_t n_true = n_dev ? *n_dev : n_rows, n_elem = plane_rows * D;  // saved[6][plane_rows][D]
-    const int64_t row0 = (int64_t)blockIdx.x * kGruRows;
-    float s_r = 0.f, s_z = 0.f, s_n = 0.f, s_nr = 0.f;
-    for (int k = rl; k < kGruRows; k += 4) {
-        const int64_t node = row0 + k;
-        if (node >= n_rows) break;
-        const int64_t i = node * D + c;
-        float *gi = g_gi + node * 3 * D, *gh = g_gh + node * 3 * D;
-        if (node >= n_true) {  // rows past the true node count (upper-bound buffers): exact zeros
-            gi[c] = gi[D + c] = gi[2 * D + c] = 0.f;
-            gh[c] = gh[D + c] = gh[2 * D + c] = 0.f;
-            g_h0d[i] = 0.f;
-            continue;
-        }
-        const float r = saved[n_elem + i], z = saved[2 * n_elem + i], nn = saved[3 * n_elem + i];
-        const float hl = saved[4 * n_elem + i], h0 = saved[5 * n_elem + i], g = g_h[i];
-        const float g_np = g * (1.f - z) * (1.f - nn * nn);  // d/d(pre-activation of n)
-        const float g_zp = g * (h0 - nn) * z * (1.f - z);
-        const float g_rp = g_np * hl * r * (1.f - r);
-        gi[c] = g_rp;
-        gi[D + c] = g_zp;
-        gi[2 * D + c] = g_np;
-        gh[c] = g_rp;
-        gh[D + c] = g_zp;
-        gh[2 * D + c] = g_np * r;
-        g_h0d[i] = g * z;
-        s_r += g_rp;
-        s_z += g_zp;
-        s_n += g_np;
-        s_nr += g_np * r;
-    }
-    if (bias_partial) {
-        sm[rl][0][c] = s_r;
-        sm[rl][1][c] = s_z;
-        sm[rl][2][c] = s_n;
-        sm[rl][3][c] = s_nr;
-        __syncthreads();
-        if (rl == 0) {
-            float *o = bias_partial + (size_t)blockIdx.x * 4 * D;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) o[q * D + c] = (sm[0][q][c] + sm[1][q][c]) + (sm[2][q][c] + sm[3][q][c]);
-        }
-    }
-}
-
-extern "C" int rg_gru_bwd_elem(int32_t hidden_dim, int64_t n_nodes, int64_t saved_plane_rows,
-                               const int64_t *n_nodes_dev, const float *g_hidden, const float *saved, float *g_gi,
-                               float *g_gh, float *g_h0_direct, float *bias_partial, void *stream) {
-    if (n_nodes < 0 || hidden_dim <= 0 || !g_hidden || !saved || !g_gi || !g_gh || !g_h0_direct) return RG_ERR_BAD_ARG;
-    if (n_nodes == 0) return RG_OK;
-    const unsigned grid = (unsigned)rg_cdiv(n_nodes, kGruRows);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t plane = saved_plane_rows > 0 ? saved_plane_rows : n_nodes;
-    if (plane < n_nodes) return RG_ERR_BAD_ARG;
-    switch (hidden_dim) {
-        case 16: k_gru_bwd_elem<16><<<grid, 64, 0, st>>>(n_nodes, plane, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
-        case 32: k_gru_bwd_elem<32><<<grid, 128, 0, st>>>(n_nodes, plane, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
-        case 48: k_gru_bwd_elem<48><<<grid, 192, 0, st>>>(n_nodes, plane, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
-        case 64: k_gru_bwd_elem<64><<<grid, 256, 0, st>>>(n_nodes, plane, n_nodes_dev, g_hidden, saved, g_gi, g_gh, g_h0_direct, bias_partial); break;
-        default: return RG_ERR_UNSUPPORTED;
-    }
-    RG_LAUNCH_CHECK();
-    return RG_OK;
-}
 
 // training forward: tensor-core kernel only (hidden_dim <= 48); also writes saved[6][n][D] =
 // {act(W_h agg) before dropout, r, z, n, W_hn h0 + b_hn, h0} for the backward pass
