@@ -46,6 +46,19 @@ def test_version_sizes_and_errors_without_gpu():
     assert lib.rg_scatter_scores(5, None, None, None, None, 3, None, None) == -1
     fr = _lib.RgFrontier(70000, 70000, 1, 1, None)
     assert lib.rg_frontier_nodes(ctypes.byref(fr), None, None, None, None) == -4
+    # the round-2 entry points: null pointers / bad sizes are refused the same way
+    assert lib.rg_node_bwd(48, 10, None, None, None, 8, None, 0, None, None, None, 10, None, None, None, None, 1, 1,
+                           None, None, None, None, None) == -1
+    assert lib.rg_node_wgrad(48, 10, None, None, 10, None, None, None, None, None, None, 8, 1, None, None, None, None,
+                             None, None, None, None, 0, None) == -1
+    assert lib.rg_attn_tables(48, 9, 10, 2, *([None] * 10)) == -1                      # attn_dim > 8
+    assert lib.rg_attn_param_grads(48, 5, 10, 2, 0, *([None] * 7), 32, *([None] * 7)) == -1   # grad_copies < 1
+    assert lib.rg_node_loss(0, 10, *([None] * 7)) == -1
+    assert lib.rg_graph_resplit(None, None, 5, 10, 2, None, None, None, None) == -1
+    assert lib.rg_get_neighbors_expand(None, None, 0, None, None, None, None, None, 0, None) == -1
+    assert lib.rg_node_wgrad_ctas() >= 148 and lib.rg_node_wgrad_out_floats(48) == 7 * 48 * 48 + 8 * 48 + 4 * 48
+    assert lib.rg_node_wgrad_out_floats(64) == 0                                       # tensor-core kernels: hidden_dim <= 48
+    assert lib.rg_edge_agg_variant(None, 48) == -1
 
 
 def test_struct_layout_matches_header():
