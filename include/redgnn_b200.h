@@ -45,6 +45,9 @@ typedef enum rg_status {
     RG_ERR_UNSUPPORTED = -2,  /* hidden_dim not in {16,32,48,64} or attn_dim > 8              */
     RG_ERR_WORKSPACE = -3,    /* workspace smaller than rg_workspace_bytes()                  */
     RG_ERR_TOO_LARGE = -4,    /* an index space of this call would exceed 2^31-1              */
+    RG_ERR_IO = -5,           /* rg_text_*: the file cannot be opened / mapped                */
+    RG_ERR_PARSE = -6,        /* rg_text_*: a line does not hold exactly three names          */
+    RG_ERR_UNKNOWN_NAME = -7, /* rg_text_*: a name is in neither entity2id nor relation2id    */
     RG_ERR_CUDA_BASE = -1000  /* -(1000 + cudaError_t) for a CUDA launch / API failure        */
 } rg_status;
 
@@ -139,6 +142,32 @@ const char *rg_strerror(int status);
 size_t rg_frontier_emask_bytes(int32_t n_query, int32_t n_ent);
 size_t rg_frontier_dict_bytes(int32_t n_query, int32_t n_ent);
 size_t rg_workspace_bytes(int32_t n_query, int32_t n_ent, int64_t n_fact);
+
+/* ---- text side of the graph store (host-only: no GPU, no stream) -----------------
+ * DataLoader.read_triples (transductive/load_data.py:58-67, inductive/load_data.py:76-86): every line
+ * of facts/train/valid/test.txt is `h, r, t = line.strip().split()` mapped through entity2id /
+ * relation2id (transductive/load_data.py:11-25 by line number, inductive/load_data.py:14-40 from
+ * "name id" files).  The caller hands both dictionaries over as flat arrays; the file is mapped
+ * read-only and parsed by `n_threads` host threads (<= 0: all cores) split at line boundaries.
+ *   lines      : as Python's text-mode iteration yields them ("\n", "\r\n" or a lone "\r" end a line;
+ *                a last line without terminator counts when it is not empty);
+ *   separators : what str.split() accepts in UTF-8 text (ASCII white space, 0x1c-0x1f, U+0085, U+00A0,
+ *                U+1680, U+2000-200A, U+2028/9, U+202F, U+205F, U+3000); names compare as bytes.
+ * Errors follow the reference's first failure in file order: a line without exactly three names is
+ * RG_ERR_PARSE (its ValueError), a name missing from its dictionary RG_ERR_UNKNOWN_NAME (its
+ * KeyError), an unreadable file RG_ERR_IO (its FileNotFoundError); *err_line = 0-based line. */
+typedef struct rg_name_table {
+    const char *bytes;       /* the names back to back (UTF-8 as in the file, no terminators)  */
+    const int64_t *off;      /* [n+1]: name k is bytes[off[k], off[k+1])                        */
+    const int32_t *id;       /* [n]: the dictionary value; a name listed twice: the later wins  */
+    int64_t n;
+} rg_name_table;
+
+int rg_text_count_lines(const char *path, int64_t *n_lines);
+/* out[cap_rows][3] int32 (h, r, t) in file order; *n_rows = lines of the file (set whenever the file
+ * can be read; RG_ERR_BAD_ARG if it exceeds cap_rows, nothing is written then). */
+int rg_text_parse_triples(const char *path, const rg_name_table *ent, const rg_name_table *rel, int32_t *out,
+                          int64_t cap_rows, int64_t *n_rows, int64_t *err_line, int32_t n_threads);
 
 /* Graph build: the CSR views of rg_graph from the fact arrays (replaces the scipy csr_matrix of
  * load_graph, transductive/load_data.py:76-81, re-run every epoch by shuffle_train :152-164).

@@ -42,6 +42,13 @@ class RgHeavy(C.Structure):
                 ("node_base", C.c_void_p), ("node_n", C.c_void_p), ("partial", C.c_void_p)]
 
 
+class RgNameTable(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("off", C.c_void_p), ("id", C.c_void_p), ("n", C.c_int64)]
+
+
+RG_ERR_BAD_ARG = -1
+RG_ERR_IO, RG_ERR_PARSE, RG_ERR_UNKNOWN_NAME = -5, -6, -7
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "rg_abi_version": (C.c_int, []),
@@ -49,6 +56,9 @@ SIGNATURES = {
     "rg_frontier_emask_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rg_frontier_dict_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rg_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int64]),
+    "rg_text_count_lines": (C.c_int, [C.c_char_p, C.POINTER(C.c_int64)]),
+    "rg_text_parse_triples": (C.c_int, [C.c_char_p, C.POINTER(RgNameTable), C.POINTER(RgNameTable), C.c_void_p,
+                                        C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32]),
     "rg_graph_build_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64]),
     "rg_graph_build": (C.c_int, [C.c_void_p] * 3 + [C.c_int32, C.c_int64] + [C.c_void_p] * 5 + [C.c_size_t, C.c_void_p]),
     "rg_graph_resplit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 4),

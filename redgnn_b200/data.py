@@ -6,40 +6,19 @@ Only the graph store and `get_neighbors` are on the accelerated path; the text p
 grouping, filters and batching below are host-side harness kept behaviour-compatible so that the
 reference's base_model.py / train.py run unchanged.
 """
-from collections import defaultdict
 import os
 
 import numpy as np
 import torch
 
 from .graph import DeviceGraph
+from .text import NameTable, filter_table, parse_triples, read_id_table as _read_id_table
 
 
 def _default_device():
     if not torch.cuda.is_available():
         return None
     return torch.device('cuda', torch.cuda.current_device())
-
-
-def _read_id_table(path, with_id):
-    table = {}
-    with open(path) as f:
-        for k, line in enumerate(f):
-            if with_id:
-                name, idx = line.strip().split()
-                table[name] = int(idx)
-            else:
-                table[line.strip()] = k
-    return table
-
-
-def _read_raw_triples(path, ent, rel):
-    out = []
-    with open(path) as f:
-        for line in f:
-            h, r, t = line.strip().split()
-            out.append([ent[h], rel[r], ent[t]])
-    return out
 
 
 def _group_queries(triples):
@@ -129,7 +108,7 @@ class TransductiveLoader(object):
         self.n_ent = len(self.entity2id)
         self.n_rel = len(self.relation2id)
 
-        self.filters = defaultdict(lambda: set())
+        self._names = (NameTable(self.entity2id), NameTable(self.relation2id))
         self.fact_triple = self.read_triples('facts.txt')
         self.train_triple = self.read_triples('train.txt')
         self.valid_triple = self.read_triples('valid.txt')
@@ -151,17 +130,16 @@ class TransductiveLoader(object):
         self.n_valid = len(self.valid_q)
         self.n_test = len(self.test_q)
 
-        for filt in self.filters:
-            self.filters[filt] = list(self.filters[filt])
+        # load_data.py:64-65 + :51-52: (h, r) -> tails and (t, r + n_rel) -> heads over all four files
+        self.filters = filter_table([self.fact_data, self.train_data, self.valid_data, self.test_data], self.n_ent)
 
         print('n_train:', self.n_train, 'n_valid:', self.n_valid, 'n_test:', self.n_test)
 
     def read_triples(self, filename):
-        triples = _read_raw_triples(os.path.join(self.task_dir, filename), self.entity2id, self.relation2id)
-        for h, r, t in triples:
-            self.filters[(h, r)].add(t)
-            self.filters[(t, r + self.n_rel)].add(h)
-        return triples
+        """load_data.py:58-67 on the host threads (rg_text_parse_triples); an (n, 3) int64 array where the
+        reference builds a list of lists.  The filter entries of the same loop are built once, in
+        __init__, from the doubled arrays."""
+        return parse_triples(os.path.join(self.task_dir, filename), *self._names)
 
     def double_triple(self, triples):
         """Inverse triples appended as one block after the originals (load_data.py:69-74).  Returns an
@@ -274,6 +252,9 @@ class InductiveLoader(object):
         self.n_ent = len(self.entity2id)
         self.n_rel = len(self.relation2id)
         self.n_ent_ind = len(self.entity2id_ind)
+        rel_names = NameTable(self.relation2id)
+        self._names = {'transductive': (NameTable(self.entity2id), rel_names),
+                       'inductive': (NameTable(self.entity2id_ind), rel_names)}
 
         self.tra_train = self.read_triples(self.trans_dir, 'train.txt')
         self.tra_valid = self.read_triples(self.trans_dir, 'valid.txt')
@@ -284,10 +265,6 @@ class InductiveLoader(object):
 
         self.val_filters = self.get_filter('valid')
         self.tst_filters = self.get_filter('test')
-        for filt in self.val_filters:
-            self.val_filters[filt] = list(self.val_filters[filt])
-        for filt in self.tst_filters:
-            self.tst_filters[filt] = list(self.tst_filters[filt])
 
         self._tra_graph = self.load_graph(self.tra_train)
         self._ind_graph = self.load_graph(self.ind_train, 'inductive')
@@ -308,11 +285,10 @@ class InductiveLoader(object):
 
     def read_triples(self, directory, filename, mode='transductive'):
         """(h,r,t) and its inverse interleaved per line (inductive/load_data.py:76-86)."""
-        ent = self.entity2id if mode == 'transductive' else self.entity2id_ind
-        out = []
-        for h, r, t in _read_raw_triples(os.path.join(directory, filename), ent, self.relation2id):
-            out.append([h, r, t])
-            out.append([t, r + self.n_rel, h])
+        a = parse_triples(os.path.join(directory, filename), *self._names[mode])
+        out = np.empty((2 * len(a), 3), dtype=np.int64)
+        out[0::2] = a
+        out[1::2, 0], out[1::2, 1], out[1::2, 2] = a[:, 2], a[:, 1] + self.n_rel, a[:, 0]
         return out
 
     def load_graph(self, triples, mode='transductive'):
@@ -356,10 +332,7 @@ class InductiveLoader(object):
         self.tra_train = self.tra_train[rand_idx]
 
     def get_filter(self, data='valid'):
-        filters = defaultdict(lambda: set())
-        groups = (self.tra_train, self.tra_valid, self.tra_test) if data == 'valid' \
-            else (self.ind_train, self.ind_valid, self.ind_test)
-        for triples in groups:
-            for h, r, t in triples:
-                filters[(h, r)].add(t)
-        return filters
+        """inductive/load_data.py:170-197; the values are lists already (:43-46)."""
+        if data == 'valid':
+            return filter_table([self.tra_train, self.tra_valid, self.tra_test], self.n_ent)
+        return filter_table([self.ind_train, self.ind_valid, self.ind_test], self.n_ent_ind)

@@ -67,6 +67,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.RgFrontier) == 8 + 3 * 8
     assert ctypes.sizeof(_lib.RgSegments) == 16 + 8 * 8 + 8
     assert ctypes.sizeof(_lib.RgHeavy) == 8 + 7 * 8
+    assert ctypes.sizeof(_lib.RgNameTable) == 4 * 8
 
 
 def test_no_cpu_fallback():
