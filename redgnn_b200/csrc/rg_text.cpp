@@ -146,7 +146,7 @@ struct Mapped {
         if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return RG_ERR_IO;
         n = (size_t)st.st_size;
         if (n == 0) return RG_OK;
-        void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);   // one pass instead of a fault per 64 KB
         if (m == MAP_FAILED) return RG_ERR_IO;
         p = (const unsigned char *)m;
         madvise(m, n, MADV_SEQUENTIAL);
