@@ -48,6 +48,7 @@ typedef enum rg_status {
     RG_ERR_IO = -5,           /* rg_text_*: the file cannot be opened / mapped                */
     RG_ERR_PARSE = -6,        /* rg_text_*: a line does not hold exactly three names          */
     RG_ERR_UNKNOWN_NAME = -7, /* rg_text_*: a name is in neither entity2id nor relation2id    */
+    RG_ERR_HOST = -8,         /* rg_text_*: host allocation failed                            */
     RG_ERR_CUDA_BASE = -1000  /* -(1000 + cudaError_t) for a CUDA launch / API failure        */
 } rg_status;
 
@@ -155,7 +156,8 @@ size_t rg_workspace_bytes(int32_t n_query, int32_t n_ent, int64_t n_fact);
  *                U+1680, U+2000-200A, U+2028/9, U+202F, U+205F, U+3000); names compare as bytes.
  * Errors follow the reference's first failure in file order: a line without exactly three names is
  * RG_ERR_PARSE (its ValueError), a name missing from its dictionary RG_ERR_UNKNOWN_NAME (its
- * KeyError), an unreadable file RG_ERR_IO (its FileNotFoundError); *err_line = 0-based line. */
+ * KeyError), an unreadable file RG_ERR_IO (its FileNotFoundError); *err_line = 0-based line.
+ * The file must not shrink while the call runs (it is mapped, not copied). */
 typedef struct rg_name_table {
     const char *bytes;       /* the names back to back (UTF-8 as in the file, no terminators)  */
     const int64_t *off;      /* [n+1]: name k is bytes[off[k], off[k+1])                        */

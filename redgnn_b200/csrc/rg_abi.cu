@@ -17,6 +17,7 @@ const char *rg_strerror(int status) {
         case RG_ERR_IO: return "file cannot be opened or mapped";
         case RG_ERR_PARSE: return "a line of a triples file does not hold exactly three names";
         case RG_ERR_UNKNOWN_NAME: return "a name of a triples file is missing from entity2id / relation2id";
+        case RG_ERR_HOST: return "host allocation failed";
         default: break;
     }
     if (status <= RG_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(RG_ERR_CUDA_BASE - status));

@@ -10,7 +10,6 @@
 #include <unistd.h>
 
 #include <algorithm>
-#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -200,12 +199,57 @@ void chunk_starts(const Mapped &f, int T, std::vector<size_t> *start) {
     }
 }
 
+// fn(k) for k in [0, T): chunk 0 on the calling thread, the others on their own threads; a chunk whose
+// thread cannot be started runs on the calling thread instead.  fn must not throw.
+template <class F>
+void run_chunks(int T, F fn) {
+    std::vector<std::thread> th;
+    th.reserve(T > 0 ? T : 0);
+    int started = 1;
+    for (int k = 1; k < T; k++) {
+        try {
+            th.emplace_back(fn, k);
+        } catch (...) {
+            break;
+        }
+        started = k + 1;
+    }
+    fn(0);
+    for (int k = started; k < T; k++) fn(k);
+    for (auto &t : th) t.join();
+}
+
 }  // namespace
 
+static int count_lines_impl(const char *path, int64_t *n_lines);
+static int parse_triples_impl(const char *path, const rg_name_table *ent, const rg_name_table *rel, int32_t *out,
+                              int64_t cap_rows, int64_t *n_rows, int64_t *err_line, int32_t n_threads);
+
+// nothing is thrown across the C boundary: a failed allocation becomes RG_ERR_HOST
 extern "C" {
 
 int rg_text_count_lines(const char *path, int64_t *n_lines) {
     if (!path || !n_lines) return RG_ERR_BAD_ARG;
+    try {
+        return count_lines_impl(path, n_lines);
+    } catch (...) {
+        return RG_ERR_HOST;
+    }
+}
+
+int rg_text_parse_triples(const char *path, const rg_name_table *ent, const rg_name_table *rel, int32_t *out,
+                          int64_t cap_rows, int64_t *n_rows, int64_t *err_line, int32_t n_threads) {
+    if (!path || !ent || !rel || !n_rows || cap_rows < 0 || (cap_rows > 0 && !out)) return RG_ERR_BAD_ARG;
+    try {
+        return parse_triples_impl(path, ent, rel, out, cap_rows, n_rows, err_line, n_threads);
+    } catch (...) {
+        return RG_ERR_HOST;
+    }
+}
+
+}  // extern "C"
+
+static int count_lines_impl(const char *path, int64_t *n_lines) {
     Mapped f;
     int rc = f.open_file(path);
     if (rc != RG_OK) return rc;
@@ -213,20 +257,15 @@ int rg_text_count_lines(const char *path, int64_t *n_lines) {
     std::vector<size_t> start;
     chunk_starts(f, T, &start);
     std::vector<int64_t> cnt(T, 0);
-    std::vector<std::thread> th;
-    for (int k = 1; k < T; k++)
-        th.emplace_back([&, k] { cnt[k] = count_lines(f.p, start[k], start[k + 1], f.n); });
-    cnt[0] = count_lines(f.p, start[0], start[1], f.n);
-    for (auto &t : th) t.join();
+    run_chunks(T, [&](int k) { cnt[k] = count_lines(f.p, start[k], start[k + 1], f.n); });
     int64_t tot = 0;
     for (int k = 0; k < T; k++) tot += cnt[k];
     *n_lines = tot;
     return RG_OK;
 }
 
-int rg_text_parse_triples(const char *path, const rg_name_table *ent, const rg_name_table *rel, int32_t *out,
-                          int64_t cap_rows, int64_t *n_rows, int64_t *err_line, int32_t n_threads) {
-    if (!path || !ent || !rel || !n_rows || cap_rows < 0 || (cap_rows > 0 && !out)) return RG_ERR_BAD_ARG;
+static int parse_triples_impl(const char *path, const rg_name_table *ent, const rg_name_table *rel, int32_t *out,
+                              int64_t cap_rows, int64_t *n_rows, int64_t *err_line, int32_t n_threads) {
     if (ent->n < 0 || rel->n < 0 || ent->n > INT32_MAX || rel->n > INT32_MAX) return RG_ERR_BAD_ARG;
     if ((ent->n > 0 && (!ent->bytes || !ent->off || !ent->id)) || (rel->n > 0 && (!rel->bytes || !rel->off || !rel->id)))
         return RG_ERR_BAD_ARG;
@@ -236,25 +275,13 @@ int rg_text_parse_triples(const char *path, const rg_name_table *ent, const rg_n
     int rc = f.open_file(path);
     if (rc != RG_OK) return rc;
     NameIndex E, R;
-    bool ok_e = true, ok_r = true;
-    {
-        std::thread tb([&] { ok_r = R.build(rel); });   // the two dictionaries are indexed side by side
-        ok_e = E.build(ent);
-        tb.join();
-    }
-    if (!ok_e || !ok_r) return RG_ERR_BAD_ARG;
+    if (!E.build(ent) || !R.build(rel)) return RG_ERR_BAD_ARG;
 
     int T = resolve_threads(n_threads, f.n);
     std::vector<size_t> start;
     chunk_starts(f, T, &start);
     std::vector<int64_t> cnt(T, 0), base(T + 1, 0);
-    {
-        std::vector<std::thread> th;
-        for (int k = 1; k < T; k++)
-            th.emplace_back([&, k] { cnt[k] = count_lines(f.p, start[k], start[k + 1], f.n); });
-        cnt[0] = count_lines(f.p, start[0], start[1], f.n);
-        for (auto &t : th) t.join();
-    }
+    run_chunks(T, [&](int k) { cnt[k] = count_lines(f.p, start[k], start[k + 1], f.n); });
     for (int k = 0; k < T; k++) base[k + 1] = base[k] + cnt[k];
     *n_rows = base[T];
     if (base[T] > cap_rows) return RG_ERR_BAD_ARG;
@@ -321,12 +348,7 @@ int rg_text_parse_triples(const char *path, const rg_name_table *ent, const rg_n
             }
         }
     };
-    {
-        std::vector<std::thread> th;
-        for (int k = 1; k < T; k++) th.emplace_back(work, k);
-        work(0);
-        for (auto &t : th) t.join();
-    }
+    run_chunks(T, work);
     for (int k = 0; k < T; k++)
         if (bad_rc[k] != RG_OK) {
             if (err_line) *err_line = bad_line[k];
@@ -334,5 +356,3 @@ int rg_text_parse_triples(const char *path, const rg_name_table *ent, const rg_n
         }
     return RG_OK;
 }
-
-}  // extern "C"
