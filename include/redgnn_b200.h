@@ -149,7 +149,8 @@ size_t rg_workspace_bytes(int32_t n_query, int32_t n_ent, int64_t n_fact);
  * of facts/train/valid/test.txt is `h, r, t = line.strip().split()` mapped through entity2id /
  * relation2id (transductive/load_data.py:11-25 by line number, inductive/load_data.py:14-40 from
  * "name id" files).  The caller hands both dictionaries over as flat arrays; the file is mapped
- * read-only and parsed by `n_threads` host threads (<= 0: all cores) split at line boundaries.
+ * read-only and parsed by `n_threads` host threads (<= 0: all cores; at most 64 and one per MiB of file)
+ * split at line boundaries.
  *   lines      : as Python's text-mode iteration yields them ("\n", "\r\n" or a lone "\r" end a line;
  *                a last line without terminator counts when it is not empty);
  *   separators : what str.split() accepts in UTF-8 text (ASCII white space, 0x1c-0x1f, U+0085, U+00A0,
