@@ -64,7 +64,9 @@ def count_lines(path):
 def parse_triples(path, entity2id, relation2id, n_threads=0):
     """(n, 3) int64 [h, r, t] of the file's lines in file order.  `entity2id` / `relation2id` are
     dicts or prebuilt `NameTable`s.  Raises what the reference's loop raises at its first bad line:
-    FileNotFoundError, ValueError (not exactly three names), KeyError (unknown name)."""
+    FileNotFoundError, ValueError (not exactly three names), KeyError (unknown name).  One difference: bytes
+    that are not valid UTF-8 are compared as they are (an unknown name, KeyError) where Python's text
+    decoding of the file would raise UnicodeDecodeError."""
     ent, rel = _as_table(entity2id), _as_table(relation2id)
     try:
         cap = (os.path.getsize(path) + 1) // 6 + 1        # "a b c\n": no line that parses is shorter than 6 bytes
