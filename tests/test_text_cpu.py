@@ -229,7 +229,8 @@ def test_fuzz_against_the_reference_loop(tmp_path):
         except (ValueError, KeyError) as e:
             return type(e).__name__
 
-    @hyp.settings(max_examples=400, deadline=None)
+    @hyp.settings(max_examples=400, deadline=None, database=None, derandomize=True,
+                  suppress_health_check=list(hyp.HealthCheck))
     @hyp.given(st.lists(st.sampled_from(alphabet), max_size=40), st.integers(1, 3))
     def run(parts, threads):
         write(path, "".join(parts))
